@@ -1,0 +1,719 @@
+// C ABI (include/loco_asr.h): handle, checkpoint ingestion, batch geometry and the encoder schedule.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/loco_asr.h"
+#include "common.cuh"
+#include "internal.h"
+
+using namespace loco;
+
+namespace {
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (int64_t s : shape) n *= s;
+        return n;
+    }
+};
+
+struct LayerW {
+    bf16 *wqkv, *wo, *w1, *w2;
+    float *bqkv, *bo, *b1, *b2, *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+};
+
+struct Buf {
+    size_t off = 0;
+    int64_t rows = 0, cols = 0;
+    int dtype = LOCO_BF16;
+};
+
+struct Layout {
+    int n_utts = 0;
+    int64_t R6 = 0, total_frames = 0, total_samples = 0;
+    int max_t0 = 0, max_t6 = 0, max_slot6 = 0, chunks = 1;
+    std::vector<UttMeta> meta;
+    size_t off_meta = 0, off_partial = 0, off_scale = 0, off_shift = 0, off_rowframe = 0;
+    std::map<std::string, Buf> bufs;
+    size_t bytes = 0;
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct loco_handle {
+    loco_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    std::string err;
+    std::map<std::string, HostTensor> host;
+    bool finalized = false;
+    std::vector<void*> allocs;
+    // device weights
+    float *w0 = nullptr, *gn_w = nullptr, *gn_b = nullptr;
+    bf16* conv_w[8] = {};
+    float *pln_w = nullptr, *pln_b = nullptr, *proj_b = nullptr;
+    bf16* proj_w = nullptr;
+    bf16* pos_w = nullptr;
+    float* pos_b = nullptr;
+    float* sin_table = nullptr;
+    int sin_rows = 0;
+    float *eln_w = nullptr, *eln_b = nullptr;
+    bf16* pe_k = nullptr;
+    std::vector<LayerW> layers;
+    // debug
+    int gemm_impl = 0;
+    int stop_after_layer = -1;
+    Layout last;
+    void* last_ws = nullptr;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(loco_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (cudaError_t)(expr);                                                            \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(h, LOCO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
+
+std::string canon_key(const char* key) {
+    std::string k(key);
+    const char* pres[] = {"speecht5.encoder.", "encoder."};
+    for (const char* p : pres) {
+        size_t n = strlen(p);
+        if (k.compare(0, n, p) == 0) {
+            k = k.substr(n);
+            break;
+        }
+    }
+    const std::string pc = "prenet.pos_conv_embed.conv.";
+    if (k == pc + "weight_g" || k == pc + "parametrizations.weight.original0") return pc + "g";
+    if (k == pc + "weight_v" || k == pc + "parametrizations.weight.original1") return pc + "v";
+    return k;
+}
+
+float bf16_bits_to_float(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+float f16_bits_to_float(uint16_t hbits) {
+    const uint32_t sign = (hbits >> 15) & 1, exp = (hbits >> 10) & 0x1f, man = hbits & 0x3ff;
+    float v;
+    if (exp == 0) v = ldexpf((float)man, -24);
+    else if (exp == 31) v = man ? NAN : INFINITY;
+    else v = ldexpf((float)(man | 0x400), (int)exp - 25);
+    return sign ? -v : v;
+}
+bf16 to_bf16_host(float f) { return __float2bfloat16_rn(f); }
+
+template <typename T>
+int upload(loco_handle* h, const std::vector<T>& v, T** out) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, v.size() * sizeof(T)));
+    h->allocs.push_back(p);
+    CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<T*>(p);
+    return 0;
+}
+
+int get(loco_handle* h, const std::string& key, std::initializer_list<int64_t> shape, const HostTensor** out) {
+    auto it = h->host.find(key);
+    if (it == h->host.end()) return fail(h, LOCO_ERR_WEIGHTS, "missing tensor: " + key);
+    std::vector<int64_t> want(shape);
+    if (it->second.shape != want) {
+        std::string s = "bad shape for " + key + ": got [";
+        for (int64_t d : it->second.shape) s += std::to_string(d) + ",";
+        s += "] want [";
+        for (int64_t d : want) s += std::to_string(d) + ",";
+        return fail(h, LOCO_ERR_WEIGHTS, s + "]");
+    }
+    *out = &it->second;
+    return 0;
+}
+
+int upload_f32(loco_handle* h, const std::string& key, std::initializer_list<int64_t> shape, float** out, float scale = 1.f) {
+    const HostTensor* t;
+    int rc = get(h, key, shape, &t);
+    if (rc) return rc;
+    std::vector<float> v(t->data);
+    if (scale != 1.f)
+        for (float& x : v) x *= scale;
+    return upload(h, v, out);
+}
+
+int upload_bf16(loco_handle* h, const std::string& key, std::initializer_list<int64_t> shape, bf16** out) {
+    const HostTensor* t;
+    int rc = get(h, key, shape, &t);
+    if (rc) return rc;
+    std::vector<bf16> v(t->data.size());
+    for (size_t i = 0; i < v.size(); ++i) v[i] = to_bf16_host(t->data[i]);
+    return upload(h, v, out);
+}
+
+// Sinusoid table, computed the way HF builds it in fp32 (modeling_speecht5.py:305-320): f_j = exp(fl(j) * fl(-ln(1e4)/383)),
+// angle = fl(p) * f_j, row = [sin | cos]; row `pad_token_id` is zero.
+int build_sin_table(loco_handle* h, int rows) {
+    const int H = kHidden, half = H / 2;
+    std::vector<float> tab((size_t)rows * H);
+    const float neg_emb = (float)(-(log(10000.0) / (double)(half - 1)));
+    std::vector<float> f(half);
+    for (int j = 0; j < half; ++j) f[j] = (float)exp((double)((float)j * neg_emb));
+    for (int p = 0; p < rows; ++p) {
+        float* r = tab.data() + (size_t)p * H;
+        for (int j = 0; j < half; ++j) {
+            const float ang = (float)p * f[j];
+            r[j] = (float)sin((double)ang);
+            r[half + j] = (float)cos((double)ang);
+        }
+    }
+    if (h->cfg.pad_token_id >= 0 && h->cfg.pad_token_id < rows)
+        memset(tab.data() + (size_t)h->cfg.pad_token_id * H, 0, H * sizeof(float));
+    float* dev = nullptr;
+    int rc = upload(h, tab, &dev);
+    if (rc) return rc;
+    h->sin_table = dev;  // an outgrown table stays in `allocs` until destroy; regrowth is rare
+    h->sin_rows = rows;
+    return 0;
+}
+
+void conv_frames(const loco_config& c, int n_samples, int* t) {
+    int64_t cur = n_samples;
+    for (int i = 0; i < c.num_conv_layers; ++i) {
+        cur = cur >= c.conv_kernel[i] ? (cur - c.conv_kernel[i]) / c.conv_stride[i] + 1 : 0;
+        t[i] = (int)cur;
+    }
+}
+
+int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L) {
+    if (n_utts < 0 || n_utts > 65535) return fail(h, LOCO_ERR_INVALID, "n_utts must be in [0, 65535]");
+    L->n_utts = n_utts;
+    L->meta.resize(n_utts);
+    int64_t row = 0, out_row = 0, off = 0;
+    for (int u = 0; u < n_utts; ++u) {
+        int t[8];
+        if (n_samples[u] <= 0) return fail(h, LOCO_ERR_INVALID, "utterance " + std::to_string(u) + " is empty");
+        conv_frames(h->cfg, n_samples[u], t);
+        if (t[6] < 1)
+            return fail(h, LOCO_ERR_INVALID,
+                        "utterance " + std::to_string(u) + " is shorter than one encoder frame (" + std::to_string(n_samples[u]) +
+                            " samples; minimum 400)");
+        int slot = 1;
+        for (int i = 0; i < 7; ++i) {
+            const int sh = 6 - i;
+            const int need = (t[i] + (1 << sh) - 1) >> sh;
+            if (need > slot) slot = need;
+        }
+        UttMeta& m = L->meta[u];
+        m.sample_off = off;
+        m.n_samples = n_samples[u];
+        m.t0 = t[0];
+        m.t6 = t[6];
+        m.row6 = (int32_t)row;
+        m.slot6 = slot;
+        m.out_row = (int32_t)out_row;
+        row += slot;
+        out_row += t[6];
+        off += n_samples[u];
+        if (t[0] > L->max_t0) L->max_t0 = t[0];
+        if (t[6] > L->max_t6) L->max_t6 = t[6];
+        if (slot > L->max_slot6) L->max_slot6 = slot;
+    }
+    if ((row << 6) > (int64_t)INT32_MAX / 2) return fail(h, LOCO_ERR_INVALID, "batch too large: more than 2^30 conv0 frames");
+    L->R6 = row;
+    L->total_frames = out_row;
+    L->total_samples = off;
+    L->chunks = wave_stats_chunks(L->max_t0);
+
+    size_t p = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = p;
+        p = align_up(p + bytes);
+        return o;
+    };
+    L->off_meta = take((size_t)n_utts * sizeof(UttMeta));
+    L->off_partial = take((size_t)n_utts * L->chunks * 65 * sizeof(double));
+    L->off_scale = take((size_t)n_utts * kConvDim * sizeof(float));
+    L->off_shift = take((size_t)n_utts * kConvDim * sizeof(float));
+    L->off_rowframe = take((size_t)L->R6 * sizeof(int32_t));
+    auto add = [&](const char* name, int64_t rows, int64_t cols, int64_t pad_rows) {
+        Buf b;
+        b.rows = rows;
+        b.cols = cols;
+        b.off = take((size_t)(rows + pad_rows) * cols * sizeof(bf16));
+        L->bufs[name] = b;
+    };
+    for (int i = 0; i < 7; ++i) {
+        char nm[16];
+        snprintf(nm, sizeof nm, "conv%d", i);
+        add(nm, L->R6 << (6 - i), kConvDim, 8);
+    }
+    add("proj_ln", L->R6, kConvDim, 0);
+    add("proj", L->R6, kHidden, 0);
+    add("pos_conv", L->R6, kHidden, 0);
+    add("x", L->R6, kHidden, 0);
+    add("qkv", L->R6, 3 * kHidden, 0);
+    add("ctx", L->R6, kHidden, 0);
+    add("attn_res", L->R6, kHidden, 0);
+    add("ln1", L->R6, kHidden, 0);
+    add("mid", L->R6, kFfn, 0);
+    add("ffn_res", L->R6, kHidden, 0);
+    L->bufs["enc_in"] = L->bufs["x"];
+    L->bytes = p;
+    return 0;
+}
+
+int run_gemm(loco_handle* h, const GemmArgs& g, cudaStream_t s) {
+    int rc = h->gemm_impl == 1 ? gemm_simt_launch(g, s) : gemm_tc_launch(g, h->num_sms, s);
+    h->launches += 1;
+    if (rc) return fail(h, LOCO_ERR_CUDA, std::string("gemm launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+#define LAUNCH(expr, n)                                                                                        \
+    do {                                                                                                       \
+        int rc_ = (expr);                                                                                      \
+        h->launches += (n);                                                                                    \
+        if (rc_) return fail(h, LOCO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)rc_)); \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int loco_abi_version(void) { return LOCO_ABI_VERSION; }
+
+void loco_default_config(loco_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->hidden_size = 768;
+    c->encoder_layers = 12;
+    c->encoder_attention_heads = 12;
+    c->encoder_ffn_dim = 3072;
+    c->num_conv_layers = 7;
+    const int k[7] = {10, 3, 3, 3, 3, 2, 2}, s[7] = {5, 2, 2, 2, 2, 2, 2};
+    for (int i = 0; i < 7; ++i) {
+        c->conv_dim[i] = 512;
+        c->conv_kernel[i] = k[i];
+        c->conv_stride[i] = s[i];
+    }
+    c->num_conv_pos_embeddings = 128;
+    c->num_conv_pos_embedding_groups = 16;
+    c->max_speech_positions = 4000;
+    c->encoder_max_relative_position = 160;
+    c->pad_token_id = 1;
+    c->feat_extract_norm_is_group = 1;
+    c->activation_is_gelu = 1;
+    c->conv_bias = 0;
+    c->layer_norm_eps = 1e-5f;
+}
+
+const char* loco_last_error(const loco_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int loco_create(const loco_config* cfg, int device, loco_handle** out) {
+    if (!cfg || !out) {
+        g_create_error = "null argument";
+        return LOCO_ERR_INVALID;
+    }
+    loco_config d;
+    loco_default_config(&d);
+    std::string bad;
+    auto chk = [&](bool ok, const char* what) {
+        if (!ok) bad += std::string(bad.empty() ? "" : ", ") + what;
+    };
+    chk(cfg->hidden_size == d.hidden_size, "hidden_size");
+    chk(cfg->encoder_attention_heads == d.encoder_attention_heads, "encoder_attention_heads");
+    chk(cfg->encoder_ffn_dim == d.encoder_ffn_dim, "encoder_ffn_dim");
+    chk(cfg->encoder_layers >= 1 && cfg->encoder_layers <= 48, "encoder_layers");
+    chk(cfg->num_conv_layers == 7, "num_conv_layers");
+    for (int i = 0; i < 7; ++i)
+        chk(cfg->conv_dim[i] == d.conv_dim[i] && cfg->conv_kernel[i] == d.conv_kernel[i] && cfg->conv_stride[i] == d.conv_stride[i],
+            "conv_dim/kernel/stride");
+    chk(cfg->num_conv_pos_embeddings == 128 && cfg->num_conv_pos_embedding_groups == 16, "num_conv_pos_embeddings/groups");
+    chk(cfg->encoder_max_relative_position == 160, "encoder_max_relative_position");
+    chk(cfg->feat_extract_norm_is_group == 1, "feat_extract_norm");
+    chk(cfg->activation_is_gelu == 1, "activation");
+    chk(cfg->conv_bias == 0, "conv_bias");
+    chk(fabsf(cfg->layer_norm_eps - 1e-5f) < 1e-9f, "layer_norm_eps");
+    chk(cfg->pad_token_id >= 0, "pad_token_id");
+    if (!bad.empty()) {
+        g_create_error = "unsupported SpeechT5 encoder config (kernels are built for the SpeechT5-base shape family): " + bad;
+        return LOCO_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        g_create_error = std::string("no usable CUDA device ") + std::to_string(device) + ": " +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range") +
+                         " (this library has no CPU fallback)";
+        return LOCO_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice/GetDeviceProperties: ") + cudaGetErrorString(e);
+        return LOCO_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = "device is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this library is sm_100a only";
+        return LOCO_ERR_CUDA;
+    }
+    loco_handle* h = new loco_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    int rc = gemm_tc_init();
+    if (!rc) rc = attention_init();
+    if (!rc) rc = posconv_init();
+    if (rc) {
+        g_create_error = std::string("kernel init failed: ") + cudaGetErrorString((cudaError_t)rc);
+        delete h;
+        return LOCO_ERR_CUDA;
+    }
+    *out = h;
+    return LOCO_OK;
+}
+
+void loco_destroy(loco_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+int loco_load_tensor(loco_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype) {
+    if (!h || !key || !data || ndim < 0 || ndim > 4) return fail(h, LOCO_ERR_INVALID, "loco_load_tensor: bad argument");
+    if (h->finalized) return fail(h, LOCO_ERR_STATE, "weights already finalized");
+    const std::string k = canon_key(key);
+    if (k == "prenet.masked_spec_embed" || k.find("pos_sinusoidal_embed") != std::string::npos) return LOCO_OK;  // ignored
+    const bool known = k.compare(0, 7, "prenet.") == 0 || k.compare(0, 16, "wrapped_encoder.") == 0;
+    if (!known) return fail(h, LOCO_ERR_WEIGHTS, "unknown tensor key: " + std::string(key));
+    HostTensor t;
+    t.shape.assign(shape, shape + ndim);
+    const int64_t n = t.numel();
+    t.data.resize((size_t)n);
+    switch (dtype) {
+        case LOCO_F32: memcpy(t.data.data(), data, (size_t)n * 4); break;
+        case LOCO_F64:
+            for (int64_t i = 0; i < n; ++i) t.data[i] = (float)((const double*)data)[i];
+            break;
+        case LOCO_BF16:
+            for (int64_t i = 0; i < n; ++i) t.data[i] = bf16_bits_to_float(((const uint16_t*)data)[i]);
+            break;
+        case LOCO_F16:
+            for (int64_t i = 0; i < n; ++i) t.data[i] = f16_bits_to_float(((const uint16_t*)data)[i]);
+            break;
+        default: return fail(h, LOCO_ERR_INVALID, "loco_load_tensor: bad dtype");
+    }
+    h->host[k] = std::move(t);
+    return LOCO_OK;
+}
+
+int loco_finalize_weights(loco_handle* h) {
+    if (!h) return LOCO_ERR_INVALID;
+    if (h->finalized) return fail(h, LOCO_ERR_STATE, "weights already finalized");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    const std::string fe = "prenet.feature_encoder.conv_layers.";
+    if ((rc = upload_f32(h, fe + "0.conv.weight", {512, 1, 10}, &h->w0))) return rc;
+    if ((rc = upload_f32(h, fe + "0.layer_norm.weight", {512}, &h->gn_w))) return rc;
+    if ((rc = upload_f32(h, fe + "0.layer_norm.bias", {512}, &h->gn_b))) return rc;
+    for (int i = 1; i < 7; ++i) {
+        const int k = h->cfg.conv_kernel[i];
+        const HostTensor* t;
+        if ((rc = get(h, fe + std::to_string(i) + ".conv.weight", {512, 512, k}, &t))) return rc;
+        // [out][in][tap] -> [out][tap*512 + in]: a K-major GEMM weight whose K index matches the contiguous
+        // strip of k input frames the implicit-GEMM A operand reads
+        std::vector<bf16> w((size_t)512 * 512 * k);
+        for (int o = 0; o < 512; ++o)
+            for (int c = 0; c < 512; ++c)
+                for (int j = 0; j < k; ++j) w[((size_t)o * k + j) * 512 + c] = to_bf16_host(t->data[((size_t)o * 512 + c) * k + j]);
+        if ((rc = upload(h, w, &h->conv_w[i]))) return rc;
+    }
+    const std::string fp = "prenet.feature_projection.";
+    if ((rc = upload_f32(h, fp + "layer_norm.weight", {512}, &h->pln_w))) return rc;
+    if ((rc = upload_f32(h, fp + "layer_norm.bias", {512}, &h->pln_b))) return rc;
+    if ((rc = upload_bf16(h, fp + "projection.weight", {768, 512}, &h->proj_w))) return rc;
+    if ((rc = upload_f32(h, fp + "projection.bias", {768}, &h->proj_b))) return rc;
+    {
+        // weight-norm fold (dim = 2): W[o][i][j] = g[j] * v[o][i][j] / ||v[:, :, j]||   (HF:355-383)
+        const HostTensor *g, *v;
+        if ((rc = get(h, "prenet.pos_conv_embed.conv.g", {1, 1, 128}, &g))) return rc;
+        if ((rc = get(h, "prenet.pos_conv_embed.conv.v", {768, 48, 128}, &v))) return rc;
+        std::vector<double> norm(128, 0.0);
+        for (size_t idx = 0; idx < v->data.size(); ++idx) norm[idx % 128] += (double)v->data[idx] * (double)v->data[idx];
+        for (double& x : norm) x = sqrt(x);
+        std::vector<bf16> w((size_t)16 * 128 * 48 * 48);  // [group][tap][out_local][in]
+        for (int o = 0; o < 768; ++o)
+            for (int c = 0; c < 48; ++c)
+                for (int j = 0; j < 128; ++j) {
+                    const float val = (float)((double)g->data[j] * (double)v->data[((size_t)o * 48 + c) * 128 + j] / norm[j]);
+                    w[(((size_t)(o / 48) * 128 + j) * 48 + (o % 48)) * 48 + c] = to_bf16_host(val);
+                }
+        if ((rc = upload(h, w, &h->pos_w))) return rc;
+        if ((rc = upload_f32(h, "prenet.pos_conv_embed.conv.bias", {768}, &h->pos_b))) return rc;
+    }
+    if ((rc = upload_f32(h, "wrapped_encoder.layer_norm.weight", {768}, &h->eln_w))) return rc;
+    if ((rc = upload_f32(h, "wrapped_encoder.layer_norm.bias", {768}, &h->eln_b))) return rc;
+    if ((rc = upload_bf16(h, "wrapped_encoder.embed_positions.pe_k.weight", {320, 64}, &h->pe_k))) return rc;
+    h->layers.resize(h->cfg.encoder_layers);
+    for (int l = 0; l < h->cfg.encoder_layers; ++l) {
+        const std::string p = "wrapped_encoder.layers." + std::to_string(l) + ".";
+        LayerW& w = h->layers[l];
+        const HostTensor *q, *k, *v, *bq, *bk, *bv;
+        if ((rc = get(h, p + "attention.q_proj.weight", {768, 768}, &q))) return rc;
+        if ((rc = get(h, p + "attention.k_proj.weight", {768, 768}, &k))) return rc;
+        if ((rc = get(h, p + "attention.v_proj.weight", {768, 768}, &v))) return rc;
+        if ((rc = get(h, p + "attention.q_proj.bias", {768}, &bq))) return rc;
+        if ((rc = get(h, p + "attention.k_proj.bias", {768}, &bk))) return rc;
+        if ((rc = get(h, p + "attention.v_proj.bias", {768}, &bv))) return rc;
+        // fused QKV; q (weight and bias) pre-scaled by head_dim^-0.5 = 0.125, exact in bf16 (HF:891)
+        std::vector<bf16> wqkv((size_t)2304 * 768);
+        std::vector<float> bqkv(2304);
+        for (size_t i = 0; i < (size_t)768 * 768; ++i) {
+            wqkv[i] = to_bf16_host(q->data[i] * 0.125f);
+            wqkv[(size_t)768 * 768 + i] = to_bf16_host(k->data[i]);
+            wqkv[(size_t)2 * 768 * 768 + i] = to_bf16_host(v->data[i]);
+        }
+        for (int i = 0; i < 768; ++i) {
+            bqkv[i] = bq->data[i] * 0.125f;
+            bqkv[768 + i] = bk->data[i];
+            bqkv[1536 + i] = bv->data[i];
+        }
+        if ((rc = upload(h, wqkv, &w.wqkv))) return rc;
+        if ((rc = upload(h, bqkv, &w.bqkv))) return rc;
+        if ((rc = upload_bf16(h, p + "attention.out_proj.weight", {768, 768}, &w.wo))) return rc;
+        if ((rc = upload_f32(h, p + "attention.out_proj.bias", {768}, &w.bo))) return rc;
+        if ((rc = upload_f32(h, p + "layer_norm.weight", {768}, &w.ln1_w))) return rc;
+        if ((rc = upload_f32(h, p + "layer_norm.bias", {768}, &w.ln1_b))) return rc;
+        if ((rc = upload_bf16(h, p + "feed_forward.intermediate_dense.weight", {3072, 768}, &w.w1))) return rc;
+        if ((rc = upload_f32(h, p + "feed_forward.intermediate_dense.bias", {3072}, &w.b1))) return rc;
+        if ((rc = upload_bf16(h, p + "feed_forward.output_dense.weight", {768, 3072}, &w.w2))) return rc;
+        if ((rc = upload_f32(h, p + "feed_forward.output_dense.bias", {768}, &w.b2))) return rc;
+        if ((rc = upload_f32(h, p + "final_layer_norm.weight", {768}, &w.ln2_w))) return rc;
+        if ((rc = upload_f32(h, p + "final_layer_norm.bias", {768}, &w.ln2_b))) return rc;
+    }
+    if ((rc = build_sin_table(h, h->cfg.max_speech_positions + h->cfg.pad_token_id + 3))) return rc;
+    h->host.clear();
+    h->finalized = true;
+    return LOCO_OK;
+}
+
+int loco_plan(loco_handle* h, const int32_t* n_samples, int n_utts, int32_t* frames, int32_t* rows, int64_t* total_frames,
+              size_t* workspace_bytes) {
+    if (!h || (!n_samples && n_utts > 0)) return fail(h, LOCO_ERR_INVALID, "loco_plan: bad argument");
+    Layout L;
+    int rc = make_layout(h, n_samples, n_utts, &L);
+    if (rc) return rc;
+    for (int u = 0; u < n_utts; ++u) {
+        if (frames) frames[u] = L.meta[u].t6;
+        if (rows) rows[u] = L.meta[u].row6;
+    }
+    if (total_frames) *total_frames = L.total_frames;
+    if (workspace_bytes) *workspace_bytes = L.bytes;
+    return LOCO_OK;
+}
+
+int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples, int n_utts, float* pooled_dev, float* hidden_dev,
+                void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h) return LOCO_ERR_INVALID;
+    if (!h->finalized) return fail(h, LOCO_ERR_STATE, "loco_encode before loco_finalize_weights");
+    if (n_utts == 0) return LOCO_OK;
+    if (!wave_dev || !n_samples || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode: null argument");
+    if ((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) != 0) return fail(h, LOCO_ERR_INVALID, "workspace must be 1024-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(wave_dev) & 3) != 0) return fail(h, LOCO_ERR_INVALID, "wave_dev must be 4-byte aligned");
+    Layout& L = h->last;
+    L = Layout();
+    int rc = make_layout(h, n_samples, n_utts, &L);
+    if (rc) return rc;
+    if (workspace_bytes < L.bytes)
+        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes) + " bytes, got " + std::to_string(workspace_bytes));
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (L.max_t6 + h->cfg.pad_token_id + 1 >= h->sin_rows) {  // HF grows its table on demand too (HF:331-333)
+        CK(cudaStreamSynchronize(s));
+        if ((rc = build_sin_table(h, L.max_t6 + h->cfg.pad_token_id + 1024))) return rc;
+    }
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
+    h->last_ws = workspace_dev;
+    auto B = [&](const char* name) { return reinterpret_cast<bf16*>(ws + L.bufs[name].off); };
+    UttMeta* meta = reinterpret_cast<UttMeta*>(ws + L.off_meta);
+    double* partial = reinterpret_cast<double*>(ws + L.off_partial);
+    float* scale = reinterpret_cast<float*>(ws + L.off_scale);
+    float* shift = reinterpret_cast<float*>(ws + L.off_shift);
+    int32_t* row_frame = reinterpret_cast<int32_t*>(ws + L.off_rowframe);
+    const int R6 = (int)L.R6;
+
+    // pageable source: the runtime stages the bytes before returning, so `L.meta` may be reused at once
+    CK(cudaMemcpyAsync(meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta), cudaMemcpyHostToDevice, s));
+    for (int i = 0; i < 6; ++i) {  // the 8 pad frames the last implicit-GEMM rows of layer i+1 may touch
+        char nm[16];
+        snprintf(nm, sizeof nm, "conv%d", i);
+        const Buf& b = L.bufs[nm];
+        CK(cudaMemsetAsync(ws + b.off + (size_t)b.rows * kConvDim * 2, 0, (size_t)8 * kConvDim * 2, s));
+    }
+    LAUNCH(launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
+
+    // ---- conv feature encoder -----------------------------------------------------------------------
+    LAUNCH(launch_wave_stats(wave_dev, meta, n_utts, L.chunks, h->w0, h->gn_w, h->gn_b, partial, scale, shift, s), 2);
+    LAUNCH(launch_conv0(wave_dev, meta, n_utts, L.max_slot6 << 6, h->w0, scale, shift, B("conv0"), s), 1);
+    for (int i = 1; i < 7; ++i) {
+        char in[16], out[16];
+        snprintf(in, sizeof in, "conv%d", i - 1);
+        snprintf(out, sizeof out, "conv%d", i);
+        const int K = h->cfg.conv_kernel[i] * kConvDim;
+        const int64_t rows_in = L.bufs[in].rows + 8;
+        GemmArgs g = {};
+        g.A = B(in);
+        g.lda = 2 * kConvDim;
+        g.a_rows_alloc = (rows_in * kConvDim - K) / (2 * kConvDim) + 1;
+        g.W = h->conv_w[i];
+        g.C = B(out);
+        g.ldc = kConvDim;
+        g.M = (int)L.bufs[out].rows;
+        g.N = kConvDim;
+        g.K = K;
+        g.epilogue = EPI_BIAS_GELU;
+        if ((rc = run_gemm(h, g, s))) return rc;
+    }
+    // ---- feature projection, positional conv, sinusoid, encoder input LayerNorm -------------------------
+    LAUNCH(launch_layernorm(B("conv6"), B("proj_ln"), h->pln_w, h->pln_b, R6, kConvDim, s), 1);
+    {
+        GemmArgs g = {};
+        g.A = B("proj_ln"); g.lda = kConvDim; g.a_rows_alloc = R6; g.W = h->proj_w; g.C = B("proj"); g.ldc = kHidden;
+        g.bias = h->proj_b; g.M = R6; g.N = kHidden; g.K = kConvDim; g.epilogue = EPI_BIAS;
+        if ((rc = run_gemm(h, g, s))) return rc;
+    }
+    LAUNCH(launch_posconv(B("proj"), h->pos_w, h->pos_b, meta, n_utts, L.max_t6, B("pos_conv"), s), 1);
+    LAUNCH(launch_prenet_ln(B("proj"), B("pos_conv"), h->sin_table, row_frame, B("x"), h->eln_w, h->eln_b, R6, s), 1);
+
+    // ---- transformer layers (post-LN) -------------------------------------------------------------------
+    const int n_layers = (int)h->layers.size();
+    for (int l = 0; l < n_layers; ++l) {
+        const LayerW& w = h->layers[l];
+        GemmArgs g = {};
+        g.A = B("x"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wqkv; g.C = B("qkv"); g.ldc = 3 * kHidden;
+        g.bias = w.bqkv; g.M = R6; g.N = 3 * kHidden; g.K = kHidden; g.epilogue = EPI_BIAS;
+        if ((rc = run_gemm(h, g, s))) return rc;
+        LAUNCH(launch_attention(B("qkv"), h->pe_k, meta, n_utts, L.max_t6, B("ctx"), s), 1);
+        g = GemmArgs();
+        g.A = B("ctx"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wo; g.C = B("attn_res"); g.ldc = kHidden;
+        g.bias = w.bo; g.R = B("x"); g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kHidden; g.epilogue = EPI_BIAS_RESIDUAL;
+        if ((rc = run_gemm(h, g, s))) return rc;
+        LAUNCH(launch_layernorm(B("attn_res"), B("ln1"), w.ln1_w, w.ln1_b, R6, kHidden, s), 1);
+        g = GemmArgs();
+        g.A = B("ln1"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.w1; g.C = B("mid"); g.ldc = kFfn;
+        g.bias = w.b1; g.M = R6; g.N = kFfn; g.K = kHidden; g.epilogue = EPI_BIAS_GELU;
+        if ((rc = run_gemm(h, g, s))) return rc;
+        g = GemmArgs();
+        g.A = B("mid"); g.lda = kFfn; g.a_rows_alloc = R6; g.W = w.w2; g.C = B("ffn_res"); g.ldc = kHidden;
+        g.bias = w.b2; g.R = B("ln1"); g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kFfn; g.epilogue = EPI_BIAS_RESIDUAL;
+        if ((rc = run_gemm(h, g, s))) return rc;
+        const bool last = (l == n_layers - 1) || (l == h->stop_after_layer);
+        if (!last) {
+            LAUNCH(launch_layernorm(B("ffn_res"), B("x"), w.ln2_w, w.ln2_b, R6, kHidden, s), 1);
+        } else {
+            // last LayerNorm fused with the masked mean-pool (+ optional compact fp32 last_hidden_state)
+            LAUNCH(launch_final_ln_pool(B("ffn_res"), w.ln2_w, w.ln2_b, meta, n_utts, pooled_dev, hidden_dev, s), 1);
+            break;
+        }
+    }
+    return LOCO_OK;
+}
+
+int loco_host_workspace_bytes(loco_handle* h, const int32_t* n_samples, int n_utts, int want_hidden, size_t* bytes) {
+    if (!h || !bytes || (!n_samples && n_utts > 0)) return fail(h, LOCO_ERR_INVALID, "loco_host_workspace_bytes: bad argument");
+    Layout L;
+    int rc = make_layout(h, n_samples, n_utts, &L);
+    if (rc) return rc;
+    *bytes = L.bytes + align_up((size_t)L.total_samples * sizeof(float)) + align_up((size_t)n_utts * kHidden * sizeof(float)) +
+             (want_hidden ? align_up((size_t)L.total_frames * kHidden * sizeof(float)) : 0);
+    return LOCO_OK;
+}
+
+int loco_encode_host(loco_handle* h, const float* wave_host, const int32_t* n_samples, int n_utts, float* pooled_host,
+                     float* hidden_host, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h) return LOCO_ERR_INVALID;
+    if (n_utts == 0) return LOCO_OK;
+    if (!wave_host || !n_samples || !pooled_host || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode_host: null argument");
+    Layout L;
+    int rc = make_layout(h, n_samples, n_utts, &L);
+    if (rc) return rc;
+    const size_t wave_bytes = (size_t)L.total_samples * sizeof(float);
+    const size_t pooled_bytes = (size_t)n_utts * kHidden * sizeof(float);
+    const size_t hidden_bytes = hidden_host ? (size_t)L.total_frames * kHidden * sizeof(float) : 0;
+    const size_t need = L.bytes + align_up(wave_bytes) + align_up(pooled_bytes) + align_up(hidden_bytes);
+    if (workspace_bytes < need)
+        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small for host encode: need " + std::to_string(need) + " bytes, got " + std::to_string(workspace_bytes));
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
+    float* wave_dev = reinterpret_cast<float*>(ws + L.bytes);
+    float* pooled_dev = reinterpret_cast<float*>(ws + L.bytes + align_up(wave_bytes));
+    float* hidden_dev = hidden_host ? reinterpret_cast<float*>(ws + L.bytes + align_up(wave_bytes) + align_up(pooled_bytes)) : nullptr;
+    CK(cudaMemcpyAsync(wave_dev, wave_host, wave_bytes, cudaMemcpyHostToDevice, s));
+    rc = loco_encode(h, wave_dev, n_samples, n_utts, pooled_dev, hidden_dev, workspace_dev, L.bytes, stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(pooled_host, pooled_dev, pooled_bytes, cudaMemcpyDeviceToHost, s));
+    if (hidden_host) CK(cudaMemcpyAsync(hidden_host, hidden_dev, hidden_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return LOCO_OK;
+}
+
+int64_t loco_launch_count(const loco_handle* h) { return h ? h->launches : 0; }
+
+int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return LOCO_ERR_INVALID;
+    if (!strcmp(name, "gemm_impl")) h->gemm_impl = (int)value;
+    else if (!strcmp(name, "stop_after_layer")) h->stop_after_layer = (int)value;
+    else return fail(h, LOCO_ERR_INVALID, std::string("unknown debug knob: ") + name);
+    return LOCO_OK;
+}
+
+int loco_debug_buffer(loco_handle* h, const char* name, void** dev_ptr, int64_t* n_rows, int64_t* n_cols, int* dtype) {
+    if (!h || !name) return LOCO_ERR_INVALID;
+    if (!h->last_ws) return fail(h, LOCO_ERR_STATE, "no encode has run yet");
+    auto it = h->last.bufs.find(name);
+    if (it == h->last.bufs.end()) return fail(h, LOCO_ERR_INVALID, std::string("unknown stage buffer: ") + name);
+    if (dev_ptr) *dev_ptr = reinterpret_cast<uint8_t*>(h->last_ws) + it->second.off;
+    if (n_rows) *n_rows = it->second.rows;
+    if (n_cols) *n_cols = it->second.cols;
+    if (dtype) *dtype = it->second.dtype;
+    return LOCO_OK;
+}
+
+int loco_debug_gemm(loco_handle* h, int impl, const void* a, int64_t lda, int64_t a_rows_alloc, const void* w, void* c,
+                    const float* bias, const void* r, int m, int n, int k, int epilogue, void* stream) {
+    if (!h) return LOCO_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    GemmArgs g = {};
+    g.A = reinterpret_cast<const bf16*>(a); g.lda = lda; g.a_rows_alloc = a_rows_alloc;
+    g.W = reinterpret_cast<const bf16*>(w); g.C = reinterpret_cast<bf16*>(c); g.ldc = n; g.bias = bias;
+    g.R = reinterpret_cast<const bf16*>(r); g.ldr = n; g.M = m; g.N = n; g.K = k; g.epilogue = epilogue;
+    const int saved = h->gemm_impl;
+    h->gemm_impl = impl;
+    int rc = run_gemm(h, g, reinterpret_cast<cudaStream_t>(stream));
+    h->gemm_impl = saved;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma with
+// the fp32 accumulator in TMEM -> tcgen05.ld epilogue (bias / exact GELU / residual) -> bf16 global stores.
+//
+// One kernel covers every GEMM-shaped stage of the encoder:
+//   a3  conv layers 1-6 as implicit GEMM (A rows overlap: lda = 2*512, K = k*512)   HF modeling_speecht5.py:210-228
+//   a4  feature projection 512 -> 768                                               HF:498-510
+//   a12 fused QKV projection 768 -> 2304 and out_proj (+ residual)                  HF:872-986
+//   a13 FFN 768 -> 3072 (+ GELU) and 3072 -> 768 (+ residual)                       HF:989-1010
+//
+// Tile: 128 (M) x 256 (N) x 64 (K) per stage, 4 smem stages (4 x 48 KB), two 256-column TMEM accumulator
+// stages so the epilogue of tile i overlaps the MMAs of tile i+1.  Roles: warp 0 = TMA producer (one lane),
+// warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (warp w owns TMEM lanes
+// 32*(w%4)..+31, one accumulator row per thread).
+#include <stdio.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace loco {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct __align__(8) Barriers {
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full[ACC_STAGES];
+    uint64_t tmem_empty[ACC_STAGES];
+    uint32_t tmem_base;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, bf16* __restrict__ C,
+               int64_t ldc, const float* __restrict__ bias, const bf16* __restrict__ R, int64_t ldr, int M, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+    uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+    Barriers* bars = reinterpret_cast<Barriers*>(smem_aligned + STAGES * STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles_n = N / BN;
+    const int n_tiles_m = (M + BM - 1) / BM;
+    const int n_tiles = n_tiles_m * n_tiles_n;
+    const int n_kb = K / BK;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&bars->full[s]), 1);
+            mbar_init(smem_u32(&bars->empty[s]), 1);
+        }
+        for (int a = 0; a < ACC_STAGES; ++a) {
+            mbar_init(smem_u32(&bars->tmem_full[a]), 1);
+            mbar_init(smem_u32(&bars->tmem_empty[a]), 128);
+        }
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles_n) * BM;
+                const int n0 = (tile % n_tiles_n) * BN;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u);
+                    const uint32_t full = smem_u32(&bars->full[stage]);
+                    mbar_arrive_expect_tx(full, STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    tma_load_2d(sa, &tma_a, full, kb * BK, m0);
+                    tma_load_2d(sa + A_STAGE_BYTES, &tma_b, full, kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(smem_u32(&bars->full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint64_t da = umma_desc_sw128_kmajor(sa);
+                    const uint64_t db = umma_desc_sw128_kmajor(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 B per K=16 step inside the 128 B swizzle atom (descriptor start is in 16 B units)
+                        umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&bars->empty[stage]));  // frees the smem stage when these MMAs retire
+                    if (kb == n_kb - 1) umma_commit(smem_u32(&bars->tmem_full[acc]));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles_n) * BM;
+            const int n0 = (tile % n_tiles_n) * BN;
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < M;
+            mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            bf16* c_row = C + (int64_t)row * ldc + n0;
+            const bf16* r_row = (EPI == EPI_BIAS_RESIDUAL) ? (R + (int64_t)row * ldr + n0) : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c * 32, v);
+                tmem_ld_wait();
+                if (c == BN / 32 - 1) {
+                    // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+                        if (bias != nullptr) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j + 4));
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        }
+                        if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+                        }
+                        if (EPI == EPI_BIAS_RESIDUAL) {
+                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(r_row + c * 32 + j));
+                            const float2 r0 = unpack_bf16(rr.x), r1 = unpack_bf16(rr.y), r2 = unpack_bf16(rr.z),
+                                         r3 = unpack_bf16(rr.w);
+                            f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+                            f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+                        }
+                        uint4 o;
+                        o.x = pack_bf16(f[0], f[1]);
+                        o.y = pack_bf16(f[2], f[3]);
+                        o.z = pack_bf16(f[4], f[5]);
+                        o.w = pack_bf16(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(c_row + c * 32 + j) = o;
+                    }
+                }
+            }
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_rows) {
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+template <int EPI>
+int launch_t(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int grid, cudaStream_t stream) {
+    gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, g.C, g.ldc, g.bias, g.R, g.ldr, g.M, g.N, g.K);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int gemm_tc_init() {
+    if (g_encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return (int)e;
+        if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return (int)cudaErrorNotSupported;
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    cudaError_t e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    return (int)e;
+}
+
+int gemm_tc_launch(const GemmArgs& g, int num_sms, cudaStream_t stream) {
+    if (g.M <= 0) return 0;
+    if (g.N % BN != 0 || g.K % BK != 0 || (g.lda * 2) % 16 != 0 || (g.ldc % 8) != 0) return (int)cudaErrorInvalidValue;
+    if (g.epilogue == EPI_BIAS_RESIDUAL && (g.R == nullptr || (g.ldr % 8) != 0)) return (int)cudaErrorInvalidValue;
+    if (g_encode == nullptr) return (int)cudaErrorNotReady;
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, g.A, (uint64_t)g.K, (uint64_t)g.a_rows_alloc, (uint64_t)g.lda, BM);
+    if (rc) return rc;
+    rc = make_map(&mb, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K, BN);
+    if (rc) return rc;
+    const int n_tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+    switch (g.epilogue) {
+        case EPI_BIAS: return launch_t<EPI_BIAS>(g, ma, mb, grid, stream);
+        case EPI_BIAS_GELU: return launch_t<EPI_BIAS_GELU>(g, ma, mb, grid, stream);
+        case EPI_BIAS_RESIDUAL: return launch_t<EPI_BIAS_RESIDUAL>(g, ma, mb, grid, stream);
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+}  // namespace loco

@@ -1,0 +1,84 @@
+// Host-side declarations shared by the kernel translation units and api.cu.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace loco {
+
+typedef __nv_bfloat16 bf16;
+
+enum GemmEpilogue : int {
+    EPI_BIAS = 0,           // C = A W^T (+ bias)
+    EPI_BIAS_GELU = 1,      // C = gelu(A W^T (+ bias))
+    EPI_BIAS_RESIDUAL = 2,  // C = A W^T + bias + R
+};
+
+// One GEMM problem: C[M, N] (bf16, row stride ldc) = epi(A[M, K] * W[N, K]^T).
+// A rows may overlap in memory (lda < K) -- that is how the strided convolutions are expressed
+// (row t of the implicit-GEMM operand is the contiguous strip of k*512 inputs starting at frame 2t).
+struct GemmArgs {
+    const bf16* A;
+    int64_t lda;          // elements between consecutive A rows
+    int64_t a_rows_alloc; // rows of A that exist in memory (TMA bound; >= M)
+    const bf16* W;        // [N, K] row-major (nn.Linear layout)
+    bf16* C;
+    int64_t ldc;
+    const float* bias;    // [N] or nullptr
+    const bf16* R;        // residual [M, N] with row stride ldr, or nullptr
+    int64_t ldr;
+    int M, N, K;
+    int epilogue;
+};
+
+// tcgen05/TMEM/TMA GEMM (gemm_tcgen05.cu).  Returns cudaError as int (0 = ok).
+int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
+int gemm_tc_launch(const GemmArgs& g, int num_sms, cudaStream_t stream);
+// Debug-only SIMT reference GEMM (gemm_simt.cu): used by the tests to cross-check the tensor path.
+int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);
+
+// ---- front end (frontend.cu) -------------------------------------------------------------------
+struct UttMeta {          // per-utterance geometry, device-resident
+    int64_t sample_off;   // first sample in the packed waveform
+    int32_t n_samples;
+    int32_t t0;           // frames after conv layer 0
+    int32_t t6;           // frames after conv layer 6 == encoder frames T
+    int32_t row6;         // first row in every [R6, *] buffer; row in layer i buffers = row6 << (6 - i)
+    int32_t slot6;        // rows reserved in [R6, *] buffers (>= t6); layer i reserves slot6 << (6 - i)
+    int32_t out_row;      // first row in the compact hidden_out buffer (prefix sum of t6)
+};
+
+int wave_stats_chunks(int max_t0);
+int launch_wave_stats(const float* wave, const UttMeta* meta, int n_utts, int chunks, const float* w0 /*[512,10]*/,
+                      const float* gn_w, const float* gn_b, double* partial /*[n, chunks, 65]*/, float* scale /*[n,512]*/,
+                      float* shift /*[n,512]*/, cudaStream_t s);
+int launch_conv0(const float* wave, const UttMeta* meta, int n_utts, int max_slot0, const float* w0, const float* scale,
+                 const float* shift, bf16* out /*[R0, 512]*/, cudaStream_t s);
+
+// ---- row-wise kernels (rowops.cu) --------------------------------------------------------------
+// y = LayerNorm(x) over `cols` (512 or 768), bf16 in / bf16 out.
+int launch_layernorm(const bf16* x, bf16* y, const float* gamma, const float* beta, int rows, int cols, cudaStream_t s);
+// y = LayerNorm(h + pc + sinusoid(frame + 2)) : end of the prenet + encoder input LayerNorm; slot padding rows -> 0.
+int launch_prenet_ln(const bf16* h, const bf16* pc, const float* sin_table, const int32_t* row_frame, bf16* y,
+                     const float* gamma, const float* beta, int rows, cudaStream_t s);
+// Final LayerNorm of the last layer fused with the masked mean-pool and the optional compact fp32 copy.
+int launch_final_ln_pool(const bf16* x, const float* gamma, const float* beta, const UttMeta* meta, int n_utts,
+                         float* pooled /*[n,768]*/, float* hidden_out_or_null, cudaStream_t s);
+// row_frame[r] = frame index of row r inside its utterance, or -1 for slot padding rows.
+int launch_row_frames(const UttMeta* meta, int n_utts, int max_slot6, int32_t* row_frame, cudaStream_t s);
+
+// ---- positional conv (posconv.cu) --------------------------------------------------------------
+// pc[r, :] = gelu(bias + grouped_conv(h)[r, :]) with zero padding at each utterance's own boundaries.
+int posconv_init();
+int launch_posconv(const bf16* h, const bf16* w /*[16][128][48 out][48 in]*/, const float* bias, const UttMeta* meta,
+                   int n_utts, int max_t6, bf16* pc, cudaStream_t s);
+
+// ---- attention (attention.cu) ------------------------------------------------------------------
+// ctx[r, h*64:(h+1)*64] = softmax_j(q_i.k_j + q_i.pe_k[clip(i-j)+160]) v_j within each utterance.
+int attention_init();
+int launch_attention(const bf16* qkv /*[R6, 2304]*/, const bf16* pe_k /*[320, 64]*/, const UttMeta* meta, int n_utts,
+                     int max_t6, bf16* ctx /*[R6, 768]*/, cudaStream_t s);
+
+}  // namespace loco

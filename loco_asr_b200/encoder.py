@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference's encoder call surface, backed by the C-ABI CUDA library.
+
+Reference call sites this class is a drop-in for (speech_text/extract_speecht5_base_embeddings_slurp.py):
+
+    model = SpeechT5ForSpeechToText.from_pretrained("microsoft/speecht5_asr").to(device)      # :98
+    model.speecht5.encoder.wrapped_encoder.load_state_dict(encoder_state_dict)                # :99
+    model.speecht5.encoder.prenet.load_state_dict(speech_prenet_state_dict)                   # :100
+    out = model.speecht5.encoder(**audios)            # audios = {input_values, attention_mask}   :108
+    embeddings = out.last_hidden_state.cpu().detach().numpy()                                 # :109
+
+``LocoSpeechT5Encoder`` plays the role of ``model.speecht5.encoder`` (HF ``SpeechT5EncoderWithSpeechPrenet``,
+modeling_speecht5.py:1341-1374): same keyword arguments, same ``.last_hidden_state`` ([B, T_max, 768] fp32),
+same ``.prenet`` / ``.wrapped_encoder`` ``load_state_dict`` entry points and checkpoint key names
+(map_speecht5_hf.py:34-168).  Extra: ``.pooled`` (mean over each utterance's own frames) and the var-len
+fast paths ``encode_packed`` / ``encode_host`` that never build a padded tensor.
+
+Semantics note: every utterance is encoded as if alone (no padding leaks into GroupNorm or
+the positional conv), which is what the reference computes for equal-length batches bit-exactly.
+
+PyTorch is used here only for device memory, streams and tensor plumbing; all arithmetic runs in
+``libloco_asr.so``.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Mapping, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import LocoSpeechT5Config
+
+_TORCH2LOCO = {torch.float32: _lib.LOCO_F32, torch.float16: _lib.LOCO_F16, torch.bfloat16: _lib.LOCO_BF16,
+               torch.float64: _lib.LOCO_F64}
+
+
+@dataclass
+class LocoEncoderOutput:
+    """Mirrors HF ``BaseModelOutput`` for the fields the reference reads, plus the pooled embedding."""
+    last_hidden_state: Optional[torch.Tensor]   # f32[B, T_max, 768], rows past an utterance's length are 0
+    pooled: torch.Tensor                        # f32[B, 768]
+    frame_lengths: torch.Tensor                 # i64[B] (cpu)
+    hidden_states = None
+    attentions = None
+
+    def __getitem__(self, i):
+        return (self.last_hidden_state,)[i]
+
+
+class _SubmoduleShim:
+    """``encoder.prenet`` / ``encoder.wrapped_encoder``: accepts the sub-module state dicts the reference
+    pickles with map_speecht5_hf.py (keys stripped of their 3 leading components, :94-99 / :157-168)."""
+
+    def __init__(self, owner: "LocoSpeechT5Encoder", prefix: str):
+        self._owner, self._prefix = owner, prefix
+
+    def load_state_dict(self, state_dict: Mapping[str, torch.Tensor], strict: bool = True):
+        self._owner._ingest({self._prefix + k: v for k, v in state_dict.items()})
+        return "<All keys matched successfully>"
+
+
+class LocoSpeechT5Encoder:
+    def __init__(self, config=None, device: "torch.device | str | int" = "cuda:0"):
+        self.config = LocoSpeechT5Config.from_hf(config) if config is not None else LocoSpeechT5Config()
+        self.config.validate()
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise _lib.LocoError(f"LocoSpeechT5Encoder runs on CUDA (sm_100a) only, got device {dev}; there is no CPU fallback")
+        if not torch.cuda.is_available():
+            raise _lib.LocoError("no CUDA device is visible; the B200 extension cannot run and there is no CPU fallback")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self._lib = _lib.load()
+        cc = _lib.LocoConfigC()
+        self._lib.loco_default_config(C.byref(cc))
+        cc.encoder_layers = self.config.encoder_layers
+        cc.max_speech_positions = self.config.max_speech_positions
+        cc.pad_token_id = self.config.pad_token_id
+        cc.layer_norm_eps = self.config.layer_norm_eps
+        h = C.c_void_p()
+        rc = self._lib.loco_create(C.byref(cc), self.device.index, C.byref(h))
+        _lib.check(self._lib, None, rc, "loco_create")
+        self._h = h
+        self._finalized = False
+        self._workspace: Optional[torch.Tensor] = None
+        self.prenet = _SubmoduleShim(self, "prenet.")
+        self.wrapped_encoder = _SubmoduleShim(self, "wrapped_encoder.")
+
+    # ------------------------------------------------------------------ lifecycle / HF-module look-alikes
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.loco_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def eval(self):
+        return self
+
+    def to(self, device=None, *a, **k):
+        if device is not None and torch.device(device).type != "cuda":
+            raise _lib.LocoError("LocoSpeechT5Encoder cannot move off the GPU (no CPU fallback)")
+        return self
+
+    def load_state_dict(self, state_dict: Mapping[str, torch.Tensor], strict: bool = True):
+        """Full-encoder dict: HF keys with or without the ``speecht5.encoder.`` prefix."""
+        self._ingest(dict(state_dict))
+        return "<All keys matched successfully>"
+
+    @classmethod
+    def from_state_dict(cls, state_dict, config=None, device="cuda:0") -> "LocoSpeechT5Encoder":
+        enc = cls(config, device)
+        enc.load_state_dict(state_dict)
+        enc.finalize()
+        return enc
+
+    def _ingest(self, sd: Dict[str, torch.Tensor]):
+        if self._finalized:
+            raise _lib.LocoError("weights are already finalized; create a new encoder to load another checkpoint")
+        for k, v in sd.items():
+            if not (k.startswith("prenet.") or k.startswith("wrapped_encoder.") or k.startswith("speecht5.encoder.")
+                    or k.startswith("encoder.")):
+                continue  # decoder / head tensors of a full-model checkpoint are not on this path
+            t = v.detach()
+            if t.dtype not in _TORCH2LOCO:
+                t = t.float()
+            t = t.cpu().contiguous()
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            if t.dtype == torch.bfloat16:
+                ptr = t.view(torch.int16).numpy().ctypes.data
+            else:
+                ptr = t.numpy().ctypes.data
+            rc = self._lib.loco_load_tensor(self._h, k.encode(), C.c_void_p(ptr), shape, t.dim(), _TORCH2LOCO[t.dtype])
+            _lib.check(self._lib, self._h, rc, f"loco_load_tensor({k})")
+
+    def finalize(self):
+        if not self._finalized:
+            rc = self._lib.loco_finalize_weights(self._h)
+            _lib.check(self._lib, self._h, rc, "loco_finalize_weights")
+            self._finalized = True
+        return self
+
+    # ------------------------------------------------------------------ geometry
+    def plan(self, n_samples: Sequence[int]):
+        ns = np.ascontiguousarray(np.asarray(n_samples, dtype=np.int32))
+        n = int(ns.shape[0])
+        frames = np.zeros(n, dtype=np.int32)
+        rows = np.zeros(n, dtype=np.int32)
+        total = C.c_int64()
+        ws = C.c_size_t()
+        rc = self._lib.loco_plan(self._h, ns.ctypes.data, n, frames.ctypes.data, rows.ctypes.data, C.byref(total), C.byref(ws))
+        _lib.check(self._lib, self._h, rc, "loco_plan")
+        return {"frames": frames, "rows": rows, "total_frames": int(total.value), "workspace_bytes": int(ws.value)}
+
+    def _get_workspace(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+        off = (-self._workspace.data_ptr()) % 1024
+        return self._workspace[off:]
+
+    # ------------------------------------------------------------------ var-len fast path (device buffers)
+    def encode_packed(self, wave: torch.Tensor, n_samples: Sequence[int], return_hidden: bool = False,
+                      out: Optional[torch.Tensor] = None):
+        """wave: f32[sum(n_samples)] on this device, utterances concatenated without padding.
+        Returns pooled f32[B, 768] (and the compact last_hidden_state f32[sum T, 768] if asked).
+        Asynchronous on the current stream."""
+        self.finalize()
+        if wave.device != self.device or wave.dtype != torch.float32 or not wave.is_contiguous():
+            raise _lib.LocoError("encode_packed wants a contiguous float32 waveform tensor on " + str(self.device))
+        ns = np.ascontiguousarray(np.asarray(n_samples, dtype=np.int32))
+        n = int(ns.shape[0])
+        if int(ns.sum()) != wave.numel():
+            raise _lib.LocoError(f"sum(n_samples)={int(ns.sum())} does not match the waveform length {wave.numel()}")
+        info = self.plan(ns)
+        ws = self._get_workspace(info["workspace_bytes"])
+        pooled = out if out is not None else torch.empty(n, self.config.hidden_size, dtype=torch.float32, device=self.device)
+        hidden = torch.empty(info["total_frames"], self.config.hidden_size, dtype=torch.float32, device=self.device) if return_hidden else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = self._lib.loco_encode(self._h, wave.data_ptr(), ns.ctypes.data, n, pooled.data_ptr(),
+                                       hidden.data_ptr() if hidden is not None else None, ws.data_ptr(),
+                                       ws.numel(), C.c_void_p(stream))
+        _lib.check(self._lib, self._h, rc, "loco_encode")
+        self._last_plan = info
+        if return_hidden:
+            return pooled, hidden, info
+        return pooled
+
+    # ------------------------------------------------------------------ host buffers in, host buffers out
+    def encode_host(self, wave_host: torch.Tensor, n_samples: Sequence[int], pooled_host: Optional[torch.Tensor] = None):
+        """wave_host: f32[sum(n_samples)] in (ideally pinned) HOST memory; returns pooled f32[B,768] on the host.
+        Includes the H2D copy of the waveforms and the D2H copy of the result; synchronous."""
+        self.finalize()
+        ns = np.ascontiguousarray(np.asarray(n_samples, dtype=np.int32))
+        n = int(ns.shape[0])
+        if wave_host.device.type != "cpu" or wave_host.dtype != torch.float32 or not wave_host.is_contiguous():
+            raise _lib.LocoError("encode_host wants a contiguous float32 CPU tensor")
+        if int(ns.sum()) != wave_host.numel():
+            raise _lib.LocoError("sum(n_samples) does not match the waveform length")
+        need = C.c_size_t()
+        rc = self._lib.loco_host_workspace_bytes(self._h, ns.ctypes.data, n, 0, C.byref(need))
+        _lib.check(self._lib, self._h, rc, "loco_host_workspace_bytes")
+        ws = self._get_workspace(int(need.value))
+        if pooled_host is None:
+            pooled_host = torch.empty(n, self.config.hidden_size, dtype=torch.float32).pin_memory()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = self._lib.loco_encode_host(self._h, wave_host.data_ptr(), ns.ctypes.data, n, pooled_host.data_ptr(), None,
+                                            ws.data_ptr(), ws.numel(), C.c_void_p(stream))
+        _lib.check(self._lib, self._h, rc, "loco_encode_host")
+        return pooled_host
+
+    # ------------------------------------------------------------------ the reference's call: encoder(**audios)
+    def __call__(self, input_values: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                 output_attentions=None, output_hidden_states=None, return_dict=None, return_last_hidden_state: bool = True,
+                 **kwargs) -> LocoEncoderOutput:
+        """``input_values`` f32[B, L_max] zero-padded, ``attention_mask`` int[B, L_max] (1 = real sample), as
+        produced by ``SpeechT5Processor(audio=..., padding="longest")`` (reference :60)."""
+        if output_attentions or output_hidden_states:
+            raise _lib.LocoError("attention maps / per-layer hidden states are never materialised by the fused kernels")
+        if input_values.dim() == 1:
+            input_values = input_values[None]
+        iv = input_values.to(self.device, dtype=torch.float32)
+        B, Lmax = iv.shape
+        if attention_mask is None:
+            lengths = np.full(B, Lmax, dtype=np.int32)
+            wave = iv.reshape(-1).contiguous()
+        else:
+            am = attention_mask.to(self.device)
+            lengths = am.sum(dim=-1).to(torch.int32).cpu().numpy()   # HF: cumsum(-1)[:, -1]
+            keep = torch.arange(Lmax, device=self.device)[None, :] < torch.as_tensor(lengths, device=self.device)[:, None]
+            wave = iv[keep].contiguous()
+        if not return_last_hidden_state:
+            pooled = self.encode_packed(wave, lengths)
+            return LocoEncoderOutput(None, pooled, torch.as_tensor(self.plan(lengths)["frames"], dtype=torch.int64))
+        pooled, hidden, info = self.encode_packed(wave, lengths, return_hidden=True)
+        frames = torch.as_tensor(info["frames"], dtype=torch.int64)
+        tmax = int(frames.max())
+        out = torch.zeros(B, tmax, self.config.hidden_size, dtype=torch.float32, device=self.device)
+        fr = frames.to(self.device)
+        keep_f = torch.arange(tmax, device=self.device)[None, :] < fr[:, None]
+        out[keep_f] = hidden
+        return LocoEncoderOutput(out, pooled, frames)
+
+    forward = __call__
+
+    # ------------------------------------------------------------------ test hooks
+    def debug_set(self, name: str, value: int):
+        rc = self._lib.loco_debug_set(self._h, name.encode(), int(value))
+        _lib.check(self._lib, self._h, rc, "loco_debug_set")
+
+    def debug_buffer(self, name: str) -> torch.Tensor:
+        """Copy of a named stage buffer of the last encode as a [rows, cols] bf16 tensor."""
+        ptr, rows, cols, dt = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int()
+        rc = self._lib.loco_debug_buffer(self._h, name.encode(), C.byref(ptr), C.byref(rows), C.byref(cols), C.byref(dt))
+        _lib.check(self._lib, self._h, rc, "loco_debug_buffer")
+        off = ptr.value - self._workspace.data_ptr()
+        nbytes = rows.value * cols.value * 2
+        return self._workspace[off:off + nbytes].view(torch.bfloat16).view(rows.value, cols.value).clone()
+
+    def debug_gemm(self, a, w, bias=None, residual=None, epilogue=_lib.EPI_BIAS, impl=0, lda=None, m=None):
+        """C = epi(A W^T): unit-test entry for the GEMM kernels (a: bf16 [rows, K] or flat with lda)."""
+        k = w.shape[1]
+        n = w.shape[0]
+        lda = lda if lda is not None else a.shape[-1]
+        m = m if m is not None else a.shape[0]
+        rows_alloc = (a.numel() - k) // lda + 1
+        c = torch.empty(m, n, dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = self._lib.loco_debug_gemm(self._h, impl, a.data_ptr(), lda, rows_alloc, w.data_ptr(), c.data_ptr(),
+                                           bias.data_ptr() if bias is not None else None,
+                                           residual.data_ptr() if residual is not None else None, m, n, k, epilogue,
+                                           C.c_void_p(stream))
+        _lib.check(self._lib, self._h, rc, "loco_debug_gemm")
+        return c
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.loco_launch_count(self._h))

@@ -1,0 +1,81 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  Generates ``tests/golden/*.npz`` from the reference's own
+implementation (the unmodified HF ``SpeechT5EncoderWithSpeechPrenet``, see oracle/hf_reference.py) on
+seeded synthetic inputs.  Run in the build container:  ``python -m oracle.make_golden``.
+
+Fixtures
+  config1_hf.npz   BASELINE.json configs[0]: 16 utterances of 2.5-3.5 s, weights seed 0, waveform seed 0.
+                   pooled f32[16,768] (mean over own frames), n_frames, first/last frame of each utterance,
+                   and the reference's literal batch_size=2 padded run (informational).
+  short_taps.npz   one 0.4 s noise utterance (T=19, all taps) and one 1.3 s utterance (T=64, three taps): stage-by-stage taps of the oracle
+                   restatement *after* it has been checked against the HF module to 2e-5.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from loco_asr_b200.synth import synth_state_dict, synth_wave, config1_lengths  # noqa: E402
+from oracle import speecht5_oracle as O  # noqa: E402
+from oracle.hf_reference import build_hf_encoder, hf_encode_unpadded, hf_encode_padded_batches  # noqa: E402
+
+TAP_KEYS = ["conv0", "conv1", "conv6", "proj_ln", "proj", "pos_conv", "prenet_out", "enc_in", "l0_qkv", "l0_ctx",
+            "l0_ln1", "l0_mid", "layer0", "layer5", "layer11"]
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth_state_dict(seed=0)
+    model = build_hf_encoder(sd)
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+
+    lengths = config1_lengths()
+    waves = [synth_wave(n, 0, i) for i, n in enumerate(lengths)]
+    hs = hf_encode_unpadded(model, waves)
+    pooled = torch.stack([h.mean(0) for h in hs]).numpy()
+    first = torch.stack([h[0] for h in hs]).numpy()
+    last = torch.stack([h[-1] for h in hs]).numpy()
+    padded = hf_encode_padded_batches(model, waves, batch_size=2)
+    pooled_padded = []
+    for b, out in enumerate(padded):
+        for j in range(out.shape[0]):
+            t = hs[2 * b + j].shape[0]
+            pooled_padded.append(out[j, :t].mean(0))
+    np.savez(os.path.join(out_dir, "config1_hf.npz"),
+             lengths=np.asarray(lengths, dtype=np.int64),
+             n_frames=np.asarray([h.shape[0] for h in hs], dtype=np.int64),
+             pooled=pooled.astype(np.float32), first_frame=first.astype(np.float32),
+             last_frame=last.astype(np.float32),
+             pooled_padded_bs2=torch.stack(pooled_padded).numpy().astype(np.float32),
+             weights_seed=0, wave_seed=0)
+
+    taps_out = {}
+    for name, n, idx in (("a", 6400, 100), ("b", 20800, 101)):
+        w = synth_wave(n, 0, idx, kind="noise" if name == "a" else "mix")
+        taps = {}
+        mine = O.encode_utterance(sd, torch.from_numpy(w), taps=taps)
+        ref = hf_encode_unpadded(model, [w])[0]
+        err = float((mine - ref).abs().max())
+        assert err < 2e-5, err
+        taps_out[f"{name}_n_samples"] = n
+        taps_out[f"{name}_idx"] = idx
+        taps_out[f"{name}_hf_last_hidden"] = ref.numpy().astype(np.float32)
+        for k in (TAP_KEYS if name == "a" else ["pos_conv", "enc_in", "layer0"]):
+            v = taps[k].numpy().astype(np.float32)
+            if k in ("conv0", "conv1"):
+                v = v[:64]  # first 64 frames are enough to pin layout + GroupNorm statistics
+            taps_out[f"{name}_{k}"] = v
+    np.savez_compressed(os.path.join(out_dir, "short_taps.npz"), **taps_out)
+    for f in os.listdir(out_dir):
+        print(f, os.path.getsize(os.path.join(out_dir, f)))
+
+
+if __name__ == "__main__":
+    main()
