@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- SpeechT5-encoder audio-seconds/second on B200 (BASELINE.json metric), one JSON line on stdout.
+
+Workload (`config.workload`): BASELINE.json configs[1] -- the SLURP-shaped synthetic set: 70,000 utterances,
+16 kHz, log-normal durations clipped to [1, 10] s (median ~2.8 s), random-init SpeechT5-base weights,
+length-bucketed into padding-free batches of <= 64k encoder frames.  A *step* is one pass of the hot path over
+one such batch; steps walk the batches in an interleaved order so any prefix is a representative length mix.
+With no flags one full pass over the set is timed (K = number of batches).
+
+  value     audio-seconds encoded per second of device time, waveforms already resident in HBM
+  e2e       same metric through the C ABI with HOST buffers (loco_encode_host): pinned-host -> device copy of
+            the step's waveforms and device -> host copy of the pooled embeddings inside the timed region
+  roofline  tcgen05 GEMM kernel: algorithmic GEMM FLOPs / its summed CUDA-event time, vs the measured bf16 peak
+  cpu_baseline / --impl reference: the reference's own CPU path (HF SpeechT5 module, batch_size=2 padded
+            loop, all host cores) on a bounded sample of the same workload.
+
+N > 1 (torchrun): every rank encodes its own 70k-utterance set (weak scaling), then ONE all-gather of the
+pooled embeddings; time = max over ranks of device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=0, help="timed steps (batches); 0 = one full pass over the set")
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", choices=["loco", "reference"], default="loco")
+    p.add_argument("--utts", type=int, default=70000)
+    p.add_argument("--max-frames", type=int, default=65536)
+    p.add_argument("--e2e-steps", type=int, default=16)
+    p.add_argument("--cpu-sample", type=int, default=96, help="utterances in the bounded CPU-baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--seed", type=int, default=1234)
+    return p.parse_args()
+
+
+WORKLOAD = "SpeechT5-base speech encoder, SLURP-shaped synthetic set (BASELINE.json configs[1]): {n} utts 1-10 s log-normal, masked mean-pool"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.mask, self.max_mhz = index, [], 0, None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while self.nv is not None and not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        reasons = [n for b, n in self.REASONS.items() if self.mask & b and n != "gpu_idle"]
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"tflops_sustained": p.get("bf16_tflops_sustained"), "tflops_burst": p.get("bf16_tflops"),
+                "hbm_gbs": p.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(lengths, sample_ids, seed, repeats=1):
+    """Time the reference's own CPU implementation (HF module, bs=2 padded loop, all cores) on `sample_ids`."""
+    from loco_asr_b200.synth import synth_state_dict, synth_wave
+    from oracle.hf_reference import build_hf_encoder, time_cpu_reference, hf_encode_unpadded
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = build_hf_encoder(synth_state_dict(seed=1))
+    waves = [synth_wave(int(lengths[i]), seed, int(i)) for i in sample_ids]
+    res = time_cpu_reference(model, waves, mode="padded_bs2", repeats=repeats)
+    return model, waves, res, hf_encode_unpadded
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from loco_asr_b200.synth import slurp_shaped_lengths
+    lengths = slurp_shaped_lengths(args.utts, args.seed)
+    order = np.argsort(lengths, kind="stable")
+    K = args.steps or 4
+    W = max(args.warmup, 1)
+    # bounded sample: the same `per_step` utterances (spread over the sorted length distribution) every step, so
+    # oneDNN's per-shape primitive setup is paid in the warm-up, not in the timed steps (favours the reference)
+    per_step = 16 if K <= 30 else max(2, int(480 / K) // 2 * 2)
+    from loco_asr_b200.synth import synth_state_dict, synth_wave
+    from oracle.hf_reference import build_hf_encoder, hf_encode_padded_batches
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = build_hf_encoder(synth_state_dict(seed=1))
+    ids = order[np.linspace(0, len(order) - 1, per_step + 2).astype(int)[1:-1]]
+    waves = [synth_wave(int(lengths[i]), args.seed, int(i)) for i in ids]
+    for s in range(W):
+        hf_encode_padded_batches(model, waves, batch_size=2)
+    tot_audio, tot_t = 0.0, 0.0
+    for s in range(K):
+        t0 = time.perf_counter()
+        hf_encode_padded_batches(model, waves, batch_size=2)
+        tot_t += time.perf_counter() - t0
+        tot_audio += sum(len(w) for w in waves) / 16000.0
+    v = tot_audio / tot_t
+    cores = torch.get_num_threads()
+    sample_desc = (f"each step = the same {per_step} utterances spread over the sorted length distribution "
+                   f"({tot_audio / K:.0f} audio-s per step), HF SpeechT5 module fp32, batch_size=2 padding=longest loop, warm shapes")
+    print(json.dumps({
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * tot_t / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(n=args.utts), "device": "cpu", "batch_size": 2, "padding": "longest"},
+        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample_desc},
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ loco arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    from loco_asr_b200 import dist as ldist
+    from loco_asr_b200.buckets import make_batches, interleaved_order, batch_flops
+    from loco_asr_b200.encoder import LocoSpeechT5Encoder
+    from loco_asr_b200.flops import encoder_flops_breakdown
+    from loco_asr_b200.synth import slurp_shaped_lengths, synth_state_dict, synth_waves_device
+
+    rank, world, local = ldist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the encoder has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+
+    enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device=dev)
+    lengths = slurp_shaped_lengths(args.utts, args.seed + rank)          # every rank owns a full set (weak scaling)
+    batches = make_batches(lengths, max_frames=args.max_frames)
+    nb = len(batches)
+    order = interleaved_order(nb)
+    W = max(args.warmup, 0)
+    K = args.steps if args.steps > 0 else nb
+    steps = [order[i % nb] for i in range(W + K)]
+    need = sorted(set(steps))
+    waves = {b: synth_waves_device(lengths[batches[b]], args.seed * 1000 + rank * 100003 + b, dev) for b in need}
+    lens = {b: np.ascontiguousarray(lengths[batches[b]].astype(np.int32)) for b in need}
+    row0 = {}
+    acc = 0
+    for b in need:
+        row0[b] = acc
+        acc += len(batches[b])
+    pooled_all = torch.zeros(acc, 768, dtype=torch.float32, device=dev)
+    audio_s = {b: float(lens[b].sum()) / 16000.0 for b in need}
+
+    def run_step(b):
+        n = len(lens[b])
+        enc.encode_packed(waves[b], lens[b], out=pooled_all[row0[b]:row0[b] + n])
+
+    for b in steps[:W]:
+        run_step(b)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    enc.profile_enable(True)
+    launches0 = enc.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for b in steps[W:]:
+        run_step(b)
+    if world > 1:   # the single collective of the path: merge pooled embeddings of all ranks
+        gathered = torch.empty(world * pooled_all.shape[0], 768, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gathered, pooled_all)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.finish()
+    prof = enc.profile_collect()
+    enc.profile_enable(False)
+    launches = enc.launch_count - launches0
+    timed_audio = sum(audio_s[b] for b in steps[W:])
+    t = torch.tensor([ms, timed_audio], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, timed_audio = float(tmax[0]), float(tsum[1])
+    value = timed_audio / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): algorithmic GEMM FLOPs / summed event time ------------
+    peaks = load_peaks()
+    fl = {"gemm": 0.0, "total": 0.0, "attention": 0.0, "pos_conv": 0.0}
+    cache = {}
+    for b in steps[W:]:
+        for n in lens[b]:
+            n = int(n)
+            if n not in cache:
+                cache[n] = encoder_flops_breakdown(n)
+            d = cache[n]
+            fl["gemm"] += d["conv1_6"] + d["proj"] + d["qkvo"] + d["ffn"]
+            fl["attention"] += d["attn"] + d["relpos"]
+            fl["pos_conv"] += d["pos_conv"]
+            fl["total"] += d["total"]
+    gemm_ms, gemm_n = prof["gemm"]
+    achieved = fl["gemm"] / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    peak = peaks["tflops_sustained"]
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMEM/TMA bf16 GEMM, all epilogues)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                "traffic": None, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                "algorithmic_flops_per_launch": fl["gemm"] / max(gemm_n, 1),
+                "share_of_step": gemm_ms / ms if ms else None}
+    stage_ms = {k: round(v[0] / K, 4) for k, v in prof.items()}
+    whole = {"tflops_per_gpu": fl["total"] / (ms / 1e3) / 1e12,
+             "frac_of_sustained_peak": fl["total"] / (ms / 1e3) / 1e12 / peak if peak else None,
+             "frac_of_burst_peak": fl["total"] / (ms / 1e3) / 1e12 / peaks["tflops_burst"] if peaks["tflops_burst"] else None}
+
+    # ---- e2e: host buffers through the C ABI ---------------------------------------------------------------------
+    E = min(args.e2e_steps, K)
+    e2e_steps = steps[W:W + E]
+    e2e_need = sorted(set(e2e_steps))
+    host_w = {b: waves[b].cpu().pin_memory() for b in e2e_need}
+    host_p = {b: torch.empty(len(lens[b]), 768, dtype=torch.float32).pin_memory() for b in e2e_need}
+    for b in e2e_steps[:2]:
+        enc.encode_host(host_w[b], lens[b], host_p[b])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for b in e2e_steps:
+        enc.encode_host(host_w[b], lens[b], host_p[b])
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    e2e_audio = sum(audio_s[b] for b in e2e_steps)
+    t = torch.tensor([e2e_ms, e2e_audio], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        e2e_ms, e2e_audio = float(tmax[0]), float(tsum[1])
+    e2e = {"value": e2e_audio / (e2e_ms / 1e3), "unit": "audio-s/s", "steps": E,
+           "h2d_bytes_per_step": int(np.mean([host_w[b].numel() * 4 for b in e2e_steps])),
+           "d2h_bytes_per_step": int(np.mean([host_p[b].numel() * 4 for b in e2e_steps])),
+           "api": "loco_encode_host (C ABI) via LocoSpeechT5Encoder.encode_host, pinned host buffers"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) + parity spot check ---------------------------------------------------
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        b0 = e2e_steps[0]
+        ids_in_batch = np.linspace(0, len(lens[b0]) - 1, 4).astype(int)
+        order_all = np.argsort(lengths, kind="stable")
+        sample_ids = order_all[np.linspace(0, len(order_all) - 1, args.cpu_sample).astype(int)]
+        model, _, res, hf_unpadded = cpu_reference_run(lengths, sample_ids, args.seed)
+        cpu_baseline = {"value": res["audio_s_per_s"], "unit": "audio-s/s", "cores": res["cores"], "kind": "reference",
+                        "sample": f"{args.cpu_sample} utterances spread over the sorted length distribution "
+                                  f"({res['audio_s']:.0f} audio-s, {res['seconds']:.1f} s of CPU), HF SpeechT5 module fp32, "
+                                  "reference-style batch_size=2 padding=longest loop"}
+        # parity of the timed GPU output against the reference module run unpadded on the same waveforms
+        cu = np.concatenate([[0], np.cumsum(lens[b0])])
+        hw = host_w[b0].numpy()
+        cos = []
+        for i in ids_in_batch:
+            ref = hf_unpadded(model, [hw[cu[i]:cu[i + 1]]])[0].mean(0)
+            cos.append(float(torch.nn.functional.cosine_similarity(ref, host_p[b0][i], dim=0)))
+        parity = {"min_pooled_cosine": min(cos), "n": len(cos), "against": "HF SpeechT5 module fp32, unpadded"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(n=args.utts), "utterances_per_gpu": int(args.utts), "batches": nb,
+                       "max_frames_per_batch": args.max_frames, "audio_s_per_step": timed_audio / K / max(world, 1),
+                       "weights": "random-init SpeechT5-base (seed 1)", "accumulate": "fp32",
+                       "l2": "inputs larger than L2 (per-step working set ~10 GB)",
+                       "parallelism": f"dp{world} utterance-sharded, one all-gather of pooled embeddings"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "stage_ms_per_step": stage_ms, "whole_step": whole, "parity": parity,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

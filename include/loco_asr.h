@@ -125,6 +125,13 @@ LOCO_API int loco_encode_host(loco_handle* h, const float* wave_host, const int3
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 LOCO_API int64_t loco_launch_count(const loco_handle* h);
 
+/* Per-stage device timing for the roofline report: when enabled every launch of loco_encode is bracketed by a
+ * CUDA event pair on the caller's stream.  loco_profile_collect synchronises the device, sums elapsed
+ * milliseconds and launch counts per category -- 0 tcgen05 GEMMs, 1 attention, 2 positional conv, 3 conv0 +
+ * GroupNorm statistics, 4 LayerNorm / pooling row kernels -- and resets the records. */
+LOCO_API int loco_profile_enable(loco_handle* h, int on);
+LOCO_API int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_t* launches);
+
 /* ---- debug / test hooks (not part of the product surface) ------------------------------------------- */
 /* name: "gemm_impl" (0 = tcgen05 [default], 1 = SIMT reference), "stop_after_layer" (-1 = run all).  */
 LOCO_API int loco_debug_set(loco_handle* h, const char* name, int64_t value);

@@ -76,6 +76,14 @@ struct loco_handle {
     Layout last;
     void* last_ws = nullptr;
     int64_t launches = 0;
+    // optional per-stage CUDA-event timing (bench.py roofline): one event pair per launch
+    bool prof_on = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct ProfRec { int cat; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    int prof_cat = -1;
+    cudaEvent_t prof_start = nullptr;
 };
 
 namespace {
@@ -282,16 +290,46 @@ int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L)
     return 0;
 }
 
+enum ProfCat { CAT_GEMM = 0, CAT_ATTENTION = 1, CAT_POSCONV = 2, CAT_FRONTEND = 3, CAT_ROWOPS = 4, CAT_COUNT = 5 };
+
+cudaEvent_t prof_event(loco_handle* h) {
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        h->ev_pool.push_back(e);
+    }
+    return h->ev_pool[h->ev_used++];
+}
+void prof_begin(loco_handle* h, int cat, cudaStream_t s) {
+    if (!h->prof_on) return;
+    h->prof_cat = cat;
+    h->prof_start = prof_event(h);
+    if (h->prof_start) cudaEventRecord(h->prof_start, s);
+}
+void prof_end(loco_handle* h, cudaStream_t s) {
+    if (!h->prof_on || !h->prof_start) return;
+    cudaEvent_t b = prof_event(h);
+    if (b) {
+        cudaEventRecord(b, s);
+        h->prof.push_back({h->prof_cat, h->prof_start, b});
+    }
+    h->prof_start = nullptr;
+}
+
 int run_gemm(loco_handle* h, const GemmArgs& g, cudaStream_t s) {
+    prof_begin(h, CAT_GEMM, s);
     int rc = h->gemm_impl == 1 ? gemm_simt_launch(g, s) : gemm_tc_launch(g, h->num_sms, s);
+    prof_end(h, s);
     h->launches += 1;
     if (rc) return fail(h, LOCO_ERR_CUDA, std::string("gemm launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     return 0;
 }
 
-#define LAUNCH(expr, n)                                                                                        \
+#define LAUNCH(cat, expr, n)                                                                                   \
     do {                                                                                                       \
+        prof_begin(h, cat, s);                                                                                 \
         int rc_ = (expr);                                                                                      \
+        prof_end(h, s);                                                                                        \
         h->launches += (n);                                                                                    \
         if (rc_) return fail(h, LOCO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)rc_)); \
     } while (0)
@@ -397,6 +435,7 @@ void loco_destroy(loco_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (void* p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
 
@@ -571,11 +610,11 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         const Buf& b = L.bufs[nm];
         CK(cudaMemsetAsync(ws + b.off + (size_t)b.rows * kConvDim * 2, 0, (size_t)8 * kConvDim * 2, s));
     }
-    LAUNCH(launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
+    LAUNCH(CAT_ROWOPS, launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
 
     // ---- conv feature encoder -----------------------------------------------------------------------
-    LAUNCH(launch_wave_stats(wave_dev, meta, n_utts, L.chunks, h->w0, h->gn_w, h->gn_b, partial, scale, shift, s), 2);
-    LAUNCH(launch_conv0(wave_dev, meta, n_utts, L.max_slot6 << 6, h->w0, scale, shift, B("conv0"), s), 1);
+    LAUNCH(CAT_FRONTEND, launch_wave_stats(wave_dev, meta, n_utts, L.chunks, h->w0, h->gn_w, h->gn_b, partial, scale, shift, s), 2);
+    LAUNCH(CAT_FRONTEND, launch_conv0(wave_dev, meta, n_utts, L.max_slot6 << 6, h->w0, scale, shift, B("conv0"), s), 1);
     for (int i = 1; i < 7; ++i) {
         char in[16], out[16];
         snprintf(in, sizeof in, "conv%d", i - 1);
@@ -596,15 +635,15 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         if ((rc = run_gemm(h, g, s))) return rc;
     }
     // ---- feature projection, positional conv, sinusoid, encoder input LayerNorm -------------------------
-    LAUNCH(launch_layernorm(B("conv6"), B("proj_ln"), h->pln_w, h->pln_b, R6, kConvDim, s), 1);
+    LAUNCH(CAT_ROWOPS, launch_layernorm(B("conv6"), B("proj_ln"), h->pln_w, h->pln_b, R6, kConvDim, s), 1);
     {
         GemmArgs g = {};
         g.A = B("proj_ln"); g.lda = kConvDim; g.a_rows_alloc = R6; g.W = h->proj_w; g.C = B("proj"); g.ldc = kHidden;
         g.bias = h->proj_b; g.M = R6; g.N = kHidden; g.K = kConvDim; g.epilogue = EPI_BIAS;
         if ((rc = run_gemm(h, g, s))) return rc;
     }
-    LAUNCH(launch_posconv(B("proj"), h->pos_w, h->pos_b, meta, n_utts, L.max_t6, B("pos_conv"), s), 1);
-    LAUNCH(launch_prenet_ln(B("proj"), B("pos_conv"), h->sin_table, row_frame, B("x"), h->eln_w, h->eln_b, R6, s), 1);
+    LAUNCH(CAT_POSCONV, launch_posconv(B("proj"), h->pos_w, h->pos_b, meta, n_utts, L.max_t6, B("pos_conv"), s), 1);
+    LAUNCH(CAT_ROWOPS, launch_prenet_ln(B("proj"), B("pos_conv"), h->sin_table, row_frame, B("x"), h->eln_w, h->eln_b, R6, s), 1);
 
     // ---- transformer layers (post-LN) -------------------------------------------------------------------
     const int n_layers = (int)h->layers.size();
@@ -614,12 +653,12 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         g.A = B("x"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wqkv; g.C = B("qkv"); g.ldc = 3 * kHidden;
         g.bias = w.bqkv; g.M = R6; g.N = 3 * kHidden; g.K = kHidden; g.epilogue = EPI_BIAS;
         if ((rc = run_gemm(h, g, s))) return rc;
-        LAUNCH(launch_attention(B("qkv"), h->pe_k, meta, n_utts, L.max_t6, B("ctx"), s), 1);
+        LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, n_utts, L.max_t6, B("ctx"), s), 1);
         g = GemmArgs();
         g.A = B("ctx"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wo; g.C = B("attn_res"); g.ldc = kHidden;
         g.bias = w.bo; g.R = B("x"); g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kHidden; g.epilogue = EPI_BIAS_RESIDUAL;
         if ((rc = run_gemm(h, g, s))) return rc;
-        LAUNCH(launch_layernorm(B("attn_res"), B("ln1"), w.ln1_w, w.ln1_b, R6, kHidden, s), 1);
+        LAUNCH(CAT_ROWOPS, launch_layernorm(B("attn_res"), B("ln1"), w.ln1_w, w.ln1_b, R6, kHidden, s), 1);
         g = GemmArgs();
         g.A = B("ln1"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.w1; g.C = B("mid"); g.ldc = kFfn;
         g.bias = w.b1; g.M = R6; g.N = kFfn; g.K = kHidden; g.epilogue = EPI_BIAS_GELU;
@@ -630,10 +669,10 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         if ((rc = run_gemm(h, g, s))) return rc;
         const bool last = (l == n_layers - 1) || (l == h->stop_after_layer);
         if (!last) {
-            LAUNCH(launch_layernorm(B("ffn_res"), B("x"), w.ln2_w, w.ln2_b, R6, kHidden, s), 1);
+            LAUNCH(CAT_ROWOPS, launch_layernorm(B("ffn_res"), B("x"), w.ln2_w, w.ln2_b, R6, kHidden, s), 1);
         } else {
             // last LayerNorm fused with the masked mean-pool (+ optional compact fp32 last_hidden_state)
-            LAUNCH(launch_final_ln_pool(B("ffn_res"), w.ln2_w, w.ln2_b, meta, n_utts, pooled_dev, hidden_dev, s), 1);
+            LAUNCH(CAT_ROWOPS, launch_final_ln_pool(B("ffn_res"), w.ln2_w, w.ln2_b, meta, n_utts, pooled_dev, hidden_dev, s), 1);
             break;
         }
     }
@@ -680,6 +719,33 @@ int loco_encode_host(loco_handle* h, const float* wave_host, const int32_t* n_sa
 }
 
 int64_t loco_launch_count(const loco_handle* h) { return h ? h->launches : 0; }
+
+int loco_profile_enable(loco_handle* h, int on) {
+    if (!h) return LOCO_ERR_INVALID;
+    h->prof_on = on != 0;
+    h->prof.clear();
+    h->ev_used = 0;
+    return LOCO_OK;
+}
+
+int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_t* launches) {
+    if (!h || !ms || !launches || n_cats < CAT_COUNT) return fail(h, LOCO_ERR_INVALID, "loco_profile_collect: need room for 5 categories");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < n_cats; ++i) {
+        ms[i] = 0.0;
+        launches[i] = 0;
+    }
+    for (const auto& r : h->prof) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cat] += (double)t;
+        launches[r.cat] += 1;
+    }
+    h->prof.clear();
+    h->ev_used = 0;
+    return LOCO_OK;
+}
 
 int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
     if (!h || !name) return LOCO_ERR_INVALID;

@@ -278,6 +278,20 @@ class LocoSpeechT5Encoder:
         _lib.check(self._lib, self._h, rc, "loco_debug_gemm")
         return c
 
+    PROFILE_CATEGORIES = ("gemm", "attention", "pos_conv", "frontend", "rowops")
+
+    def profile_enable(self, on: bool = True):
+        rc = self._lib.loco_profile_enable(self._h, 1 if on else 0)
+        _lib.check(self._lib, self._h, rc, "loco_profile_enable")
+
+    def profile_collect(self):
+        """{category: (milliseconds, launches)} since the last collect (synchronises the device)."""
+        ms = (C.c_double * 5)()
+        n = (C.c_int64 * 5)()
+        rc = self._lib.loco_profile_collect(self._h, 5, ms, n)
+        _lib.check(self._lib, self._h, rc, "loco_profile_collect")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.PROFILE_CATEGORIES)}
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.loco_launch_count(self._h))

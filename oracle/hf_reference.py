@@ -61,7 +61,7 @@ def time_cpu_reference(model, waves: Sequence[np.ndarray], mode: str = "padded_b
     """Wall-clock audio-seconds/second of the reference CPU path on all host cores."""
     torch.set_num_threads(os.cpu_count() or 1)
     fn = hf_encode_padded_batches if mode == "padded_bs2" else hf_encode_unpadded
-    fn(model, waves[:2])  # warm-up
+    fn(model, waves)  # warm-up over the same shapes (oneDNN builds its primitives per input shape)
     t0 = time.perf_counter()
     for _ in range(repeats):
         fn(model, waves)

@@ -1,0 +1,106 @@
+"""CPU: host-side logic -- config validation, FLOP model, bucketing / sharding, synthetic data, GELU approximation."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from loco_asr_b200.buckets import make_batches, shard_batches, batch_flops, interleaved_order, frames_of
+from loco_asr_b200.config import LocoSpeechT5Config
+from loco_asr_b200.flops import encoder_flops, encoder_flops_breakdown
+from loco_asr_b200.synth import slurp_shaped_lengths, synth_wave, synth_state_dict, config1_lengths
+
+
+def test_config_defaults_match_hf():
+    from transformers import SpeechT5Config
+    hf = SpeechT5Config()
+    cfg = LocoSpeechT5Config.from_hf(hf)
+    assert cfg == LocoSpeechT5Config()
+    assert cfg.num_frames(48000) == 149 and cfg.min_samples == 400
+
+
+def test_config_rejects_other_shapes():
+    for bad in ({"hidden_size": 1024}, {"feat_extract_norm": "layer"}, {"conv_bias": True}, {"hidden_act": "relu"},
+                {"conv_kernel": (10, 3, 3, 3, 3, 3, 2)}, {"encoder_max_relative_position": 64}):
+        with pytest.raises(ValueError):
+            LocoSpeechT5Config.from_hf({**LocoSpeechT5Config().to_dict(), **bad})
+
+
+def test_flop_model_matches_baseline_table():
+    # BASELINE.md section 3
+    for sec, gflop in ((1, 13.90), (3, 43.19), (5, 73.13), (10, 151.07), (30, 508.89), (60, 1183.85)):
+        assert abs(encoder_flops(16000 * sec) / 1e9 - gflop) < 0.01, sec
+    d = encoder_flops_breakdown(48000)
+    assert abs(d["conv1_6"] / d["total"] - 0.339) < 0.002
+    assert abs((d["qkvo"] + d["ffn"]) / d["total"] - 0.586) < 0.002
+
+
+def test_slurp_shaped_lengths():
+    l = slurp_shaped_lengths(70000, 1234)
+    assert l.min() >= 16000 and l.max() <= 160000
+    assert 2.6 < np.median(l) / 16000 < 3.0
+    assert np.array_equal(l, slurp_shaped_lengths(70000, 1234))
+    assert config1_lengths()[0] == 40000 and config1_lengths()[-1] == 56000 and sum(config1_lengths()) == 48 * 16000
+
+
+def test_batches_cover_every_utterance_once():
+    l = slurp_shaped_lengths(5000, 7)
+    batches = make_batches(l, max_frames=16384)
+    allidx = np.concatenate(batches)
+    assert sorted(allidx.tolist()) == list(range(5000))
+    fr = frames_of(l) + 2
+    for b in batches:
+        assert fr[b].sum() <= 16384 or len(b) == 1
+    # length-sorted: batch maxima are non-decreasing
+    mx = [l[b].max() for b in batches]
+    assert mx == sorted(mx)
+
+
+def test_ragged_and_tiny_batches():
+    assert make_batches([], 1024) == []
+    one = make_batches([160000], max_frames=100)   # a single utterance larger than the budget still forms a batch
+    assert len(one) == 1 and one[0].tolist() == [0]
+
+
+def test_flop_balanced_sharding():
+    l = slurp_shaped_lengths(20000, 3)
+    batches = make_batches(l, max_frames=16384)
+    costs = batch_flops(l, batches)
+    for world in (2, 4, 8):
+        shards = shard_batches(costs, world)
+        assert sorted(sum(shards, [])) == list(range(len(batches)))
+        load = np.array([costs[s].sum() for s in shards])
+        assert load.max() / load.mean() < 1.08, (world, load)
+        assert shards == shard_batches(costs, world)     # deterministic on every rank
+
+
+def test_interleaved_order_is_a_permutation():
+    for n in (1, 2, 3, 10, 179, 180, 256):
+        assert sorted(interleaved_order(n)) == list(range(n))
+
+
+def test_synth_wave_is_deterministic():
+    a, b = synth_wave(16000, 5, 9), synth_wave(16000, 5, 9)
+    assert np.array_equal(a, b) and a.dtype == np.float32 and np.abs(a).max() < 1.0
+    assert not np.array_equal(a, synth_wave(16000, 5, 10))
+
+
+def test_state_dict_has_hf_keys():
+    from oracle.hf_reference import build_hf_encoder
+    sd = synth_state_dict(seed=0)
+    model = build_hf_encoder(sd)     # raises on any missing / unexpected key
+    assert set(sd) - {"prenet.masked_spec_embed"} <= set(model.state_dict())
+
+
+def test_gelu_rational_form_error_bound():
+    """numpy emulation (fp32) of csrc/common.cuh gelu_erf vs exact erf GELU."""
+    from scipy.special import erf
+    v = np.linspace(-12, 12, 400001).astype(np.float32)
+    z = np.abs(v) * np.float32(0.70710678)
+    t = (np.float32(1) / (np.float32(1) + np.float32(0.3275911) * z)).astype(np.float32)
+    p = t * (np.float32(0.254829592) + t * (np.float32(-0.284496736) + t * (np.float32(1.421413741) + t * (
+        np.float32(-1.453152027) + t * np.float32(1.061405429)))))
+    pe = p * np.exp(-(z * z)).astype(np.float32)
+    g = np.float32(0.5) * v * np.where(v < 0, pe, np.float32(2) - pe)
+    ref = 0.5 * v.astype(np.float64) * (1 + erf(v.astype(np.float64) / math.sqrt(2)))
+    assert np.abs(g - ref).max() < 1e-6
