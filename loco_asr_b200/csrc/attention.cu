@@ -5,12 +5,18 @@
 //   ctx_i   = sum_j softmax_j(S[i, :]) v_j        over the keys of the SAME utterance only
 //
 // The reference materialises pe_k[clip(i-j)+160] as a [T, T, 64] tensor (575 MB at 30 s) and contracts it
-// with q; here the bias goes through the equivalent table  QT = Q . pe_k^T  ([64 queries, 320]) computed once
-// per CTA on the tensor cores and kept in shared memory, and the T x T score matrix never exists: keys/values
-// stream through a double-buffered cp.async pipeline with an online softmax in registers.
+// with q; here the bias goes through the equivalent table  QT = Q . pe_k^T  computed once per CTA on the tensor
+// cores -- only the table columns this query tile can reach, kept in shared memory as fp16 -- and the T x T
+// score matrix never exists: an online softmax runs in registers while keys / values stream by.
+//
 // Variable-length utterances: one CTA per (64-query tile, head, utterance); no padding, no mask tensor.
-// Round 1 uses mma.sync for QK^T / QT / PV (1.9 % + 1.9 % of FLOPs at 3 s); moving S and O into TMEM with
-// tcgen05 is the planned next step for the long-context configs.
+// Everything the CTA consumes (needed pe_k chunks, then K and V tiles) is ONE stream of 32-row x 64 tiles pulled
+// through a 5-deep cp.async ring with a single __syncthreads per tile; at 3 s utterances the kernel is latency-
+// not math-bound (ncu r1a: 15 us per CTA for ~3 us of MMA), so prefetch depth and CTAs/SM (3-4, was 2) are what
+// count.  The MMAs are mma.sync (1.9 % + 1.9 % of FLOPs at 3 s); moving S and O into TMEM with tcgen05 is the
+// planned next step for the long-context configs.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -18,18 +24,21 @@ namespace loco {
 
 namespace {
 
-constexpr int AQ = 64;    // queries per CTA (16 per warp)
-constexpr int AK = 32;    // keys per pipeline stage
-constexpr int ALD = 72;   // padded bf16 row length of Q/K/V/pe tiles (144 B: conflict-free ldmatrix)
-constexpr int QT_LD = 324;  // fp32 row length of the bias table
-constexpr int A_SMEM = AQ * ALD * 2            // Q
-                       + 2 * 2 * AK * ALD * 2  // K, V double buffered (also stages pe_k chunks)
-                       + AQ * QT_LD * 4;       // QT
+constexpr int AQ = 64;       // queries per CTA (16 per warp)
+constexpr int AT = 32;       // rows per streamed tile (pe_k rows, keys, or values)
+constexpr int ALD = 72;      // padded bf16 row length (144 B: conflict-free ldmatrix)
+constexpr int ARING = 5;     // ring depth (prefetch distance 4 tiles)
+constexpr int TILE_ELEMS = AT * ALD;
 constexpr int QKV_LD = 3 * kHidden;
 
-// copy `rows` x 64 bf16 from global (row stride ld) into a padded smem tile; rows >= valid are zero-filled
-__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld, int rows, int valid, int tid) {
-    for (int i = tid; i < rows * 8; i += 128) {
+__host__ __device__ constexpr int attn_smem_bytes(int qt_cols) {
+    return AQ * ALD * 2 + ARING * TILE_ELEMS * 2 + AQ * (qt_cols + 8) * 2;
+}
+
+// copy 32 rows x 64 bf16 from global (row stride ld) into a padded smem tile; rows >= valid are zero-filled
+__device__ __forceinline__ void load_tile32(bf16* dst, const bf16* src, int64_t ld, int valid, int tid) {
+#pragma unroll
+    for (int i = tid; i < AT * 8; i += 128) {
         const int r = i >> 3, c = i & 7;
         const bool ok = r < valid;
         cp_async_16(smem_u32(dst + r * ALD + c * 8), src + (int64_t)(ok ? r : 0) * ld + c * 8, ok);
@@ -37,7 +46,7 @@ __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld
 }
 
 __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ pe_k,
-                                                        const UttMeta* __restrict__ meta, bf16* __restrict__ ctx) {
+                                                        const UttMeta* __restrict__ meta, bf16* __restrict__ ctx, int qt_cols) {
     const UttMeta m = meta[blockIdx.z];
     const int T = m.t6;
     const int i0 = blockIdx.x * AQ;
@@ -45,8 +54,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
     const int head = blockIdx.y;
     extern __shared__ __align__(16) uint8_t smem[];
     bf16* sq = reinterpret_cast<bf16*>(smem);
-    bf16* skv = sq + AQ * ALD;                               // [2 stages][K | V][AK][ALD]
-    float* sqt = reinterpret_cast<float*>(skv + 4 * AK * ALD);
+    bf16* ring = sq + AQ * ALD;
+    __half* sqt = reinterpret_cast<__half*>(ring + ARING * TILE_ELEMS);
+    const int qt_ld = qt_cols + 8;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gq = lane >> 2, tq = lane & 3;
 
@@ -54,52 +64,44 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
     const bf16* k_g = qkv + (int64_t)m.row6 * QKV_LD + kHidden + head * kHeadDim;
     const bf16* v_g = k_g + kHidden;
 
-    // ---- phase 0: Q tile + first pe_k chunk ------------------------------------------------------
-    load_tile(sq, q_g, QKV_LD, AQ, T - i0, tid);
-    load_tile(skv, pe_k, kHeadDim, 64, 64, tid);  // 64 pe rows fill the K|V halves of stage 0
-    cp_async_commit();
+    // table columns this tile can reach: rel = i - j, i in [i0, min(i0+63, T-1)], j in [0, T-1]
+    const int i_hi = min(i0 + AQ - 1, T - 1);
+    const int c_lo = max(i0 - (T - 1), -kMaxRel) + kMaxRel;
+    const int c_hi = min(i_hi, kMaxRel - 1) + kMaxRel;
+    const int chunk_lo = c_lo / AT;
+    const int n_pe = c_hi / AT - chunk_lo + 1;   // <= qt_cols / 32 by construction of qt_cols on the host
+    const int cbase = chunk_lo * AT;
+    const int n_kv = (T + AT - 1) / AT;
+    const int n_tiles = n_pe + 2 * n_kv;         // stream: pe chunks, then K0 V0 K1 V1 ...
 
-    // ---- phase 1: QT[64, 320] = Q . pe_k^T, 5 chunks of 64 table rows ----------------------------
-    uint32_t qf[4][4];  // Q fragments for the 4 k-steps (dims 0..63), reused by both phases
+    auto issue = [&](int s) {
+        if (s < n_tiles) {
+            bf16* dst = ring + (s % ARING) * TILE_ELEMS;
+            if (s < n_pe) {
+                load_tile32(dst, pe_k + (int64_t)(chunk_lo + s) * AT * kHeadDim, kHeadDim, AT, tid);
+            } else {
+                const int kv = (s - n_pe) >> 1;
+                const bf16* src = ((s - n_pe) & 1) ? v_g : k_g;
+                load_tile32(dst, src + (int64_t)kv * AT * QKV_LD, QKV_LD, T - kv * AT, tid);
+            }
+        }
+        cp_async_commit();
+    };
+
+    // prologue: Q tile rides in the first group
+    for (int i = tid; i < AQ * 8; i += 128) {
+        const int r = i >> 3, c = i & 7;
+        const bool ok = r < T - i0;
+        cp_async_16(smem_u32(sq + r * ALD + c * 8), q_g + (int64_t)(ok ? r : 0) * QKV_LD + c * 8, ok);
+    }
+#pragma unroll
+    for (int s = 0; s < ARING - 1; ++s) issue(s);
+
+    uint32_t qf[4][4];  // Q fragments for the 4 k-steps (dims 0..63), reused by every tile
     const int a_row = warp * 16 + (lane & 15);
     const int a_col = (lane >> 4) * 8;
     const int b_row = (lane & 7) + ((lane >> 4) << 3);
     const int b_col = ((lane >> 3) & 1) * 8;
-    for (int chunk = 0; chunk < kRelCols / 64; ++chunk) {
-        if (chunk + 1 < kRelCols / 64)
-            load_tile(skv + ((chunk + 1) & 1) * 2 * AK * ALD, pe_k + (int64_t)(chunk + 1) * 64 * kHeadDim, kHeadDim, 64, 64, tid);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        if (chunk == 0) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qf[ks], smem_u32(sq + a_row * ALD + ks * 16 + a_col));
-        }
-        const bf16* spe = skv + (chunk & 1) * 2 * AK * ALD;
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {  // pairs of 8-column n-tiles: 64 table rows per chunk
-            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t b[4];
-                ldmatrix_x4(b, smem_u32(spe + (np * 16 + b_row) * ALD + ks * 16 + b_col));
-                const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
-                mma_16816(c0, qf[ks], b0);
-                mma_16816(c1, qf[ks], b1);
-            }
-            float* r0 = sqt + (warp * 16 + gq) * QT_LD + chunk * 64 + np * 16 + tq * 2;
-            float* r1 = r0 + 8 * QT_LD;
-            r0[0] = c0[0]; r0[1] = c0[1]; r1[0] = c0[2]; r1[1] = c0[3];
-            r0[8] = c1[0]; r0[9] = c1[1]; r1[8] = c1[2]; r1[9] = c1[3];
-        }
-        __syncthreads();
-    }
-
-    // ---- phase 2: stream keys / values ------------------------------------------------------------
-    const int n_kv = (T + AK - 1) / AK;
-    load_tile(skv, k_g, QKV_LD, AK, T, tid);
-    load_tile(skv + AK * ALD, v_g, QKV_LD, AK, T, tid);
-    cp_async_commit();
 
     float o[8][4];
 #pragma unroll
@@ -108,101 +110,119 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
         for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
     float row_max[2] = {-INFINITY, -INFINITY};
     float row_sum[2] = {0.f, 0.f};
-    const int qi[2] = {i0 + warp * 16 + gq, i0 + warp * 16 + gq + 8};  // global query index of c0/c1 vs c2/c3
-    const float* qt_row[2] = {sqt + (warp * 16 + gq) * QT_LD, sqt + (warp * 16 + gq + 8) * QT_LD};
+    uint32_t pf[2][4];  // P as A-operand fragments for the two 16-key k-steps of the current key tile
+    const int qi[2] = {min(i0 + warp * 16 + gq, T - 1), min(i0 + warp * 16 + gq + 8, T - 1)};  // clamped: rows >= T are never stored
+    const __half* qt_row[2] = {sqt + (warp * 16 + gq) * qt_ld, sqt + (warp * 16 + gq + 8) * qt_ld};
     constexpr float kLog2e = 1.4426950408889634f;
 
-    for (int kv = 0; kv < n_kv; ++kv) {
-        const int j0 = kv * AK;
-        if (kv + 1 < n_kv) {
-            bf16* nxt = skv + ((kv + 1) & 1) * 2 * AK * ALD;
-            load_tile(nxt, k_g + (int64_t)(j0 + AK) * QKV_LD, QKV_LD, AK, T - j0 - AK, tid);
-            load_tile(nxt + AK * ALD, v_g + (int64_t)(j0 + AK) * QKV_LD, QKV_LD, AK, T - j0 - AK, tid);
+    for (int s = 0; s < n_tiles; ++s) {
+        cp_async_wait<ARING - 2>();
+        __syncthreads();            // tile s has landed for everyone; everyone is done with tile s-1
+        issue(s + ARING - 1);       // refill the slot tile s-1 occupied
+        const bf16* tile = ring + (s % ARING) * TILE_ELEMS;
+        if (s == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qf[ks], smem_u32(sq + a_row * ALD + ks * 16 + a_col));
         }
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        const bf16* sk = skv + (kv & 1) * 2 * AK * ALD;
-        const bf16* sv = sk + AK * ALD;
-
-        // S = Q K^T : 16 x 32 per warp
-        float s[4][4];
-#pragma unroll
-        for (int n = 0; n < 4; ++n)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) s[n][e] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+        if (s < n_pe) {
+            // ---- QT[:, chunk] = Q . pe_k[chunk]^T  (16 x 32 per warp), stored as fp16 ----------------------
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
-                uint32_t b[4];
-                ldmatrix_x4(b, smem_u32(sk + (np * 16 + b_row) * ALD + ks * 16 + b_col));
-                const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
-                mma_16816(s[np * 2], qf[ks], b0);
-                mma_16816(s[np * 2 + 1], qf[ks], b1);
+                float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t b[4];
+                    ldmatrix_x4(b, smem_u32(tile + (np * 16 + b_row) * ALD + ks * 16 + b_col));
+                    const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+                    mma_16816(c0, qf[ks], b0);
+                    mma_16816(c1, qf[ks], b1);
+                }
+                __half* r0 = sqt + (warp * 16 + gq) * qt_ld + s * AT + np * 16 + tq * 2;
+                __half* r1 = r0 + 8 * qt_ld;
+                *reinterpret_cast<__half2*>(r0) = __floats2half2_rn(c0[0], c0[1]);
+                *reinterpret_cast<__half2*>(r1) = __floats2half2_rn(c0[2], c0[3]);
+                *reinterpret_cast<__half2*>(r0 + 8) = __floats2half2_rn(c1[0], c1[1]);
+                *reinterpret_cast<__half2*>(r1 + 8) = __floats2half2_rn(c1[2], c1[3]);
+            }
+            if (s == n_pe - 1) __syncwarp();   // a warp reads back only the QT rows it wrote itself
+        } else if (((s - n_pe) & 1) == 0) {
+            // ---- key tile: S = Q K^T (+ bias), online softmax, P fragments ------------------------------
+            const int j0 = ((s - n_pe) >> 1) * AT;
+            float sc[4][4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sc[n][e] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                    uint32_t b[4];
+                    ldmatrix_x4(b, smem_u32(tile + (np * 16 + b_row) * ALD + ks * 16 + b_col));
+                    const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+                    mma_16816(sc[np * 2], qf[ks], b0);
+                    mma_16816(sc[np * 2 + 1], qf[ks], b1);
+                }
+            }
+            float mx[2] = {row_max[0], row_max[1]};
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = e >> 1;
+                    const int j = j0 + n * 8 + tq * 2 + (e & 1);
+                    int rel = qi[r] - j;
+                    rel = max(-kMaxRel, min(kMaxRel - 1, rel)) + kMaxRel - cbase;
+                    const float v = j < T ? (sc[n][e] + __half2float(qt_row[r][rel])) * kLog2e : -INFINITY;
+                    sc[n][e] = v;
+                    mx[r] = fmaxf(mx[r], v);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            }
+            float corr[2], ps[2] = {0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                corr[r] = ex2_approx(row_max[r] - mx[r]);   // first tile: exp2(-inf) = 0
+                row_max[r] = mx[r];
+            }
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                float p[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    p[e] = ex2_approx(sc[n][e] - mx[e >> 1]);
+                    ps[e >> 1] += p[e];
+                }
+                pf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
+                pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) row_sum[r] = row_sum[r] * corr[r] + ps[r];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                o[n][0] *= corr[0]; o[n][1] *= corr[0];
+                o[n][2] *= corr[1]; o[n][3] *= corr[1];
+            }
+        } else {
+            // ---- value tile: O += P V ([key][dim] storage; ldmatrix.trans yields the (k = key, n = dim) operand)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {
+                    uint32_t b[4];
+                    const int key = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                    const int dim = dp * 16 + (lane >> 4) * 8;
+                    ldmatrix_x4_trans(b, smem_u32(tile + key * ALD + dim));
+                    const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+                    mma_16816(o[dp * 2], pf[kk], b0);
+                    mma_16816(o[dp * 2 + 1], pf[kk], b1);
+                }
             }
         }
-        // + relative-position bias, key mask, running max
-        float mx[2] = {row_max[0], row_max[1]};
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = e >> 1;
-                const int j = j0 + n * 8 + tq * 2 + (e & 1);
-                int rel = qi[r] - j;
-                rel = max(-kMaxRel, min(kMaxRel - 1, rel)) + kMaxRel;
-                const float v = j < T ? s[n][e] + qt_row[r][rel] : -INFINITY;
-                s[n][e] = v;
-                mx[r] = fmaxf(mx[r], v);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-        }
-        float corr[2], ps[2] = {0.f, 0.f};
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            corr[r] = exp2f((row_max[r] - mx[r]) * kLog2e);  // first tile: exp2(-inf) = 0
-            row_max[r] = mx[r];
-        }
-        uint32_t pf[2][4];  // P as A-operand fragments for the two 16-key k-steps
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-            float p[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = e >> 1;
-                p[e] = exp2f((s[n][e] - mx[r]) * kLog2e);
-                ps[r] += p[e];
-            }
-            pf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
-            pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) row_sum[r] = row_sum[r] * corr[r] + ps[r];
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            o[n][0] *= corr[0]; o[n][1] *= corr[0];
-            o[n][2] *= corr[1]; o[n][3] *= corr[1];
-        }
-        // O += P V : V tile is [key][dim]; ldmatrix.trans yields the (k = key, n = dim) operand
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-#pragma unroll
-            for (int dp = 0; dp < 4; ++dp) {
-                uint32_t b[4];
-                const int key = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int dim = dp * 16 + (lane >> 4) * 8;
-                ldmatrix_x4_trans(b, smem_u32(sv + key * ALD + dim));
-                const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
-                mma_16816(o[dp * 2], pf[kk], b0);
-                mma_16816(o[dp * 2 + 1], pf[kk], b1);
-            }
-        }
-        __syncthreads();
     }
 
     // ---- epilogue ---------------------------------------------------------------------------------
@@ -211,25 +231,36 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
         float l = row_sum[r];
         l += __shfl_xor_sync(0xffffffffu, l, 1);
         l += __shfl_xor_sync(0xffffffffu, l, 2);
-        if (qi[r] >= T) continue;
+        const int row = i0 + warp * 16 + gq + r * 8;
+        if (row >= T) continue;
         const float inv = 1.0f / l;
-        bf16* orow = ctx + (int64_t)(m.row6 + qi[r]) * kHidden + head * kHeadDim;
+        bf16* orow = ctx + (int64_t)(m.row6 + row) * kHidden + head * kHeadDim;
 #pragma unroll
         for (int n = 0; n < 8; ++n)
             *reinterpret_cast<uint32_t*>(orow + n * 8 + tq * 2) = pack_bf16(o[n][r * 2] * inv, o[n][r * 2 + 1] * inv);
     }
 }
 
+// columns of the bias table a 64-query tile can need when no utterance in the batch exceeds max_t6 frames
+int qt_cols_for(int max_t6) {
+    int width = max_t6 + AQ - 1;
+    if (width > kRelCols) width = kRelCols;
+    int chunks = (width - 1 + AT - 1) / AT + 1;   // worst-case alignment of [c_lo, c_hi] against 32-column chunks
+    if (chunks > kRelCols / AT) chunks = kRelCols / AT;
+    return chunks * AT;
+}
+
 }  // namespace
 
 int attention_init() {
-    return (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM);
+    return (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(kRelCols));
 }
 
 int launch_attention(const bf16* qkv, const bf16* pe_k, const UttMeta* meta, int n_utts, int max_t6, bf16* ctx, cudaStream_t s) {
     if (n_utts <= 0 || max_t6 <= 0) return 0;
+    const int qt_cols = qt_cols_for(max_t6);
     dim3 grid((max_t6 + AQ - 1) / AQ, kHeads, n_utts);
-    attention_kernel<<<grid, 128, A_SMEM, s>>>(qkv, pe_k, meta, ctx);
+    attention_kernel<<<grid, 128, attn_smem_bytes(qt_cols), s>>>(qkv, pe_k, meta, ctx, qt_cols);
     return (int)cudaGetLastError();
 }
 

@@ -30,19 +30,22 @@ constexpr float kLnEps = 1e-5f;
 // ---------------------------------------------------------------------------------------------
 // math
 // ---------------------------------------------------------------------------------------------
-// Exact-erf GELU (ACT2FN["gelu"]) through the Abramowitz-Stegun 7.1.26 rational form:
-// |erf error| <= 1.5e-7, measured |gelu error| <= 4.3e-7 over [-12, 12] (tests/test_host_logic.py),
-// far below bf16 resolution.  ~14 FP32 instructions + 2 MUFU; no cancellation on the negative side.
+// GELU (ACT2FN["gelu"], exact-erf form) evaluated as  v * sigmoid(2 u(v)),  u an odd quintic fitted so that
+// tanh(u(v)) == erf(v / sqrt 2) to 2.5e-5 in GELU units over the whole real line (tests/test_host_logic.py;
+// v^2 is clamped at 64 where the sigmoid has long saturated, keeping u monotone).  The sigmoid form has no
+// cancellation on the negative side.  9 FP32 instructions + 2 MUFU (ex2, rcp) instead of ~17 for a rational
+// erf -- the GELU epilogues (conv layers, FFN1) are issue-bound, not MMA-bound, so this is what sets their speed.
+// Max |error| vs exact: 2.6e-5 absolute, two orders below the bf16 rounding of the stored activation.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float gelu_erf(float v) {
-    const float z = fabsf(v) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(t, 1.061405429f, -1.453152027f);
-    p = fmaf(t, p, 1.421413741f);
-    p = fmaf(t, p, -0.284496736f);
-    p = fmaf(t, p, 0.254829592f);
-    p *= t;
-    const float pe = p * exp2f(-z * z * 1.4426950408889634f);
-    return 0.5f * v * (v < 0.f ? pe : 2.0f - pe);
+    const float v2 = fminf(v * v, 64.0f);
+    float t = fmaf(v2, 0.0010142630552579922f, -0.10677572400266595f);
+    t = fmaf(v2, t, -2.3011213394570755f);
+    return __fdividef(v, 1.0f + ex2_approx(v * t));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -166,6 +169,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Wait for the outstanding tcgen05.ld's, then pin `r` behind the wait: the empty volatile asm statements give the
+// compiler a data dependency it cannot hoist above the wait (the loads write the registers asynchronously).
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
+}
 
 // Shared-memory matrix descriptor for a K-major operand tile written by TMA with SWIZZLE_128B:
 // rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), version 1 (Blackwell), layout type 2.

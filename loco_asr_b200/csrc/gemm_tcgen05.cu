@@ -9,8 +9,10 @@
 //
 // Tile: 128 (M) x 256 (N) x 64 (K) per stage, 4 smem stages (4 x 48 KB), two 256-column TMEM accumulator
 // stages so the epilogue of tile i overlaps the MMAs of tile i+1.  Roles: warp 0 = TMA producer (one lane),
-// warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (warp w owns TMEM lanes
-// 32*(w%4)..+31, one accumulator row per thread).
+// warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator, warps 4-11 = epilogue: warp w owns TMEM lanes
+// 32*(w%4)..+31 (one accumulator row per thread) and column half (w-4)/4, i.e. two warps per SM sub-partition so
+// the epilogue's dependent FP32/MUFU chains overlap (with one warp per sub-partition the GELU epilogue, not
+// the MMA, set the pace: ncu r1a, tensor pipe 14 % active on FFN1).
 #include <stdio.h>
 
 #include "common.cuh"
@@ -29,7 +31,8 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct __align__(8) Barriers {
@@ -65,7 +68,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
             mbar_init(smem_u32(&bars->tmem_full[a]), 1);
-            mbar_init(smem_u32(&bars->tmem_empty[a]), 128);
+            mbar_init(smem_u32(&bars->tmem_empty[a]), NUM_EPI_WARPS * 32);
         }
         mbar_fence_init();
         fence_proxy_async_smem();
@@ -127,25 +130,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ===================== epilogue: TMEM -> registers -> global =====================
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int q = warp & 3;             // TMEM lane quadrant this warp may access
+        const int half = (warp - 4) >> 2;   // which 128 of the tile's 256 columns
+        constexpr int CHUNKS = BN / 32 / 2; // 32-column chunks per warp
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles_n) * BM;
-            const int n0 = (tile % n_tiles_n) * BN;
+            const int n0 = (tile % n_tiles_n) * BN + half * (BN / 2);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < M;
             mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
             bf16* c_row = C + (int64_t)row * ldc + n0;
             const bf16* r_row = (EPI == EPI_BIAS_RESIDUAL) ? (R + (int64_t)row * ldr + n0) : nullptr;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_row + c * 32, v);
-                tmem_ld_wait();
-                if (c == BN / 32 - 1) {
+            uint32_t v[2][32];
+            tmem_ld_32x32(t_row, v[0]);
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                tmem_ld_wait(v[c & 1]);
+                if (c + 1 < CHUNKS) {
+                    tmem_ld_32x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);   // next chunk in flight during the math
+                } else {
                     // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
@@ -155,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int j = 0; j < 32; j += 8) {
                         float f[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c & 1][j + e]);
                         if (bias != nullptr) {
                             const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j));
                             const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j + 4));
