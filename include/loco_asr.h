@@ -94,7 +94,7 @@ LOCO_API const char* loco_last_error(const loco_handle* h); /* h may be NULL: re
  * `data` is HOST memory, contiguous, row-major, `shape[ndim]`. */
 LOCO_API int loco_load_tensor(loco_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype);
 
-/* Checks that every tensor arrived, folds weight-norm, scales q_proj by head_dim^-0.5, fuses q/k/v,
+/* Checks that every tensor arrived, folds weight-norm, scales q_proj by head_dim^-0.5 * log2(e), fuses q/k/v,
  * re-lays conv weights tap-major, casts GEMM operands to bf16 and uploads. */
 LOCO_API int loco_finalize_weights(loco_handle* h);
 
@@ -133,7 +133,8 @@ LOCO_API int loco_profile_enable(loco_handle* h, int on);
 LOCO_API int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_t* launches);
 
 /* ---- debug / test hooks (not part of the product surface) ------------------------------------------- */
-/* name: "gemm_impl" (0 = tcgen05 [default], 1 = SIMT reference), "stop_after_layer" (-1 = run all).  */
+/* name: "gemm_impl" (0 = tcgen05 [default], 1 = SIMT reference), "posconv_impl" (0 = tcgen05 [default],
+ * 1 = mma.sync cross-check), "stop_after_layer" (-1 = run all).  */
 LOCO_API int loco_debug_set(loco_handle* h, const char* name, int64_t value);
 /* After an encode: device pointer / geometry of a named stage buffer inside the caller's workspace
  * ("conv0".."conv6", "proj_ln", "proj", "pos_conv", "enc_in", "qkv", "ctx", "attn_res", "ln1", "mid",

@@ -41,6 +41,8 @@ struct Layout {
     int64_t R6 = 0, total_frames = 0, total_samples = 0;
     int max_t0 = 0, max_t6 = 0, max_slot6 = 0, chunks = 1;
     std::vector<UttMeta> meta;
+    std::vector<PcTile> pc_tiles;
+    size_t off_pctiles = 0;
     size_t off_meta = 0, off_partial = 0, off_scale = 0, off_shift = 0, off_rowframe = 0;
     std::map<std::string, Buf> bufs;
     size_t bytes = 0;
@@ -63,7 +65,8 @@ struct loco_handle {
     bf16* conv_w[8] = {};
     float *pln_w = nullptr, *pln_b = nullptr, *proj_b = nullptr;
     bf16* proj_w = nullptr;
-    bf16* pos_w = nullptr;
+    bf16* pos_w = nullptr;      // [g][tap][out][in]          (mma.sync debug kernel)
+    bf16* pos_w_tc = nullptr;   // [g][tap][in/8][out][in%8]  (tcgen05 kernel: per-tap UMMA B operand)
     float* pos_b = nullptr;
     float* sin_table = nullptr;
     int sin_rows = 0;
@@ -72,6 +75,7 @@ struct loco_handle {
     std::vector<LayerW> layers;
     // debug
     int gemm_impl = 0;
+    int posconv_impl = 0;
     int stop_after_layer = -1;
     Layout last;
     void* last_ws = nullptr;
@@ -242,6 +246,7 @@ int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L)
         row += slot;
         out_row += t[6];
         off += n_samples[u];
+        for (int f = 0; f < t[6]; f += 128) L->pc_tiles.push_back({m.row6 + f, f, t[6], 0});
         if (t[0] > L->max_t0) L->max_t0 = t[0];
         if (t[6] > L->max_t6) L->max_t6 = t[6];
         if (slot > L->max_slot6) L->max_slot6 = slot;
@@ -259,6 +264,7 @@ int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L)
         return o;
     };
     L->off_meta = take((size_t)n_utts * sizeof(UttMeta));
+    L->off_pctiles = take(L->pc_tiles.size() * sizeof(PcTile));
     L->off_partial = take((size_t)n_utts * L->chunks * 65 * sizeof(double));
     L->off_scale = take((size_t)n_utts * kConvDim * sizeof(float));
     L->off_shift = take((size_t)n_utts * kConvDim * sizeof(float));
@@ -422,6 +428,8 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
     int rc = gemm_tc_init();
     if (!rc) rc = attention_init();
     if (!rc) rc = posconv_init();
+    if (!rc) rc = posconv_tc_init();
+    if (!rc) rc = frontend_init();
     if (rc) {
         g_create_error = std::string("kernel init failed: ") + cudaGetErrorString((cudaError_t)rc);
         delete h;
@@ -501,14 +509,18 @@ int loco_finalize_weights(loco_handle* h) {
         std::vector<double> norm(128, 0.0);
         for (size_t idx = 0; idx < v->data.size(); ++idx) norm[idx % 128] += (double)v->data[idx] * (double)v->data[idx];
         for (double& x : norm) x = sqrt(x);
-        std::vector<bf16> w((size_t)16 * 128 * 48 * 48);  // [group][tap][out_local][in]
+        std::vector<bf16> w((size_t)16 * 128 * 48 * 48);     // [group][tap][out_local][in]
+        std::vector<bf16> wt((size_t)16 * 128 * 48 * 48);    // [group][tap][in / 8][out_local][in % 8]
         for (int o = 0; o < 768; ++o)
             for (int c = 0; c < 48; ++c)
                 for (int j = 0; j < 128; ++j) {
                     const float val = (float)((double)g->data[j] * (double)v->data[((size_t)o * 48 + c) * 128 + j] / norm[j]);
-                    w[(((size_t)(o / 48) * 128 + j) * 48 + (o % 48)) * 48 + c] = to_bf16_host(val);
+                    const size_t gj = (size_t)(o / 48) * 128 + j;
+                    w[(gj * 48 + (o % 48)) * 48 + c] = to_bf16_host(val);
+                    wt[((gj * 6 + c / 8) * 48 + (o % 48)) * 8 + (c % 8)] = to_bf16_host(val);
                 }
         if ((rc = upload(h, w, &h->pos_w))) return rc;
+        if ((rc = upload(h, wt, &h->pos_w_tc))) return rc;
         if ((rc = upload_f32(h, "prenet.pos_conv_embed.conv.bias", {768}, &h->pos_b))) return rc;
     }
     if ((rc = upload_f32(h, "wrapped_encoder.layer_norm.weight", {768}, &h->eln_w))) return rc;
@@ -525,16 +537,18 @@ int loco_finalize_weights(loco_handle* h) {
         if ((rc = get(h, p + "attention.q_proj.bias", {768}, &bq))) return rc;
         if ((rc = get(h, p + "attention.k_proj.bias", {768}, &bk))) return rc;
         if ((rc = get(h, p + "attention.v_proj.bias", {768}, &bv))) return rc;
-        // fused QKV; q (weight and bias) pre-scaled by head_dim^-0.5 = 0.125, exact in bf16 (HF:891)
+        // fused QKV; q (weight and bias) pre-scaled by head_dim^-0.5 (HF:891) times log2(e), so the attention
+        // kernel's scores (q.k and q.pe_k are both linear in q) come out in log2 units and its softmax is a bare ex2
+        const float kQScale = 0.125f * 1.4426950408889634f;
         std::vector<bf16> wqkv((size_t)2304 * 768);
         std::vector<float> bqkv(2304);
         for (size_t i = 0; i < (size_t)768 * 768; ++i) {
-            wqkv[i] = to_bf16_host(q->data[i] * 0.125f);
+            wqkv[i] = to_bf16_host(q->data[i] * kQScale);
             wqkv[(size_t)768 * 768 + i] = to_bf16_host(k->data[i]);
             wqkv[(size_t)2 * 768 * 768 + i] = to_bf16_host(v->data[i]);
         }
         for (int i = 0; i < 768; ++i) {
-            bqkv[i] = bq->data[i] * 0.125f;
+            bqkv[i] = bq->data[i] * kQScale;
             bqkv[768 + i] = bk->data[i];
             bqkv[1536 + i] = bv->data[i];
         }
@@ -604,6 +618,8 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
 
     // pageable source: the runtime stages the bytes before returning, so `L.meta` may be reused at once
     CK(cudaMemcpyAsync(meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta), cudaMemcpyHostToDevice, s));
+    PcTile* pc_tiles = reinterpret_cast<PcTile*>(ws + L.off_pctiles);
+    CK(cudaMemcpyAsync(pc_tiles, L.pc_tiles.data(), L.pc_tiles.size() * sizeof(PcTile), cudaMemcpyHostToDevice, s));
     for (int i = 0; i < 6; ++i) {  // the 8 pad frames the last implicit-GEMM rows of layer i+1 may touch
         char nm[16];
         snprintf(nm, sizeof nm, "conv%d", i);
@@ -642,7 +658,10 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         g.bias = h->proj_b; g.M = R6; g.N = kHidden; g.K = kConvDim; g.epilogue = EPI_BIAS;
         if ((rc = run_gemm(h, g, s))) return rc;
     }
-    LAUNCH(CAT_POSCONV, launch_posconv(B("proj"), h->pos_w, h->pos_b, meta, n_utts, L.max_t6, B("pos_conv"), s), 1);
+    if (h->posconv_impl == 1)
+        LAUNCH(CAT_POSCONV, launch_posconv(B("proj"), h->pos_w, h->pos_b, meta, n_utts, L.max_t6, B("pos_conv"), s), 1);
+    else
+        LAUNCH(CAT_POSCONV, launch_posconv_tc(B("proj"), h->pos_w_tc, h->pos_b, pc_tiles, (int)L.pc_tiles.size(), B("pos_conv"), s), 1);
     LAUNCH(CAT_ROWOPS, launch_prenet_ln(B("proj"), B("pos_conv"), h->sin_table, row_frame, B("x"), h->eln_w, h->eln_b, R6, s), 1);
 
     // ---- transformer layers (post-LN) -------------------------------------------------------------------
@@ -750,6 +769,7 @@ int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_t* launch
 int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
     if (!h || !name) return LOCO_ERR_INVALID;
     if (!strcmp(name, "gemm_impl")) h->gemm_impl = (int)value;
+    else if (!strcmp(name, "posconv_impl")) h->posconv_impl = (int)value;
     else if (!strcmp(name, "stop_after_layer")) h->stop_after_layer = (int)value;
     else return fail(h, LOCO_ERR_INVALID, std::string("unknown debug knob: ") + name);
     return LOCO_OK;

@@ -1,8 +1,10 @@
 // Fused (flash-style) self-attention with SpeechT5's query-dependent relative-position bias
 // (SpeechT5Attention, HF modeling_speecht5.py:872-986; SpeechT5RelativePositionalEncoding, HF:425-441).
 //
-//   S[i, j] = q_i . k_j + q_i . pe_k[clip(i - j, -160, 159) + 160]       (q already scaled by 1/8, HF:891)
+//   S[i, j] = q_i . k_j + q_i . pe_k[clip(i - j, -160, 159) + 160]
 //   ctx_i   = sum_j softmax_j(S[i, :]) v_j        over the keys of the SAME utterance only
+// (q arrives scaled by head_dim^-0.5 * log2(e): the 1/8 of HF:891 and the exp -> exp2 conversion are folded into
+//  the q projection at weight-load time, so scores are in log2 units and the softmax is a bare ex2.)
 //
 // The reference materialises pe_k[clip(i-j)+160] as a [T, T, 64] tensor (575 MB at 30 s) and contracts it
 // with q; here the bias goes through the equivalent table  QT = Q . pe_k^T  computed once per CTA on the tensor
@@ -12,8 +14,9 @@
 // Variable-length utterances: one CTA per (64-query tile, head, utterance); no padding, no mask tensor.
 // Everything the CTA consumes (needed pe_k chunks, then K and V tiles) is ONE stream of 32-row x 64 tiles pulled
 // through a 5-deep cp.async ring with a single __syncthreads per tile; at 3 s utterances the kernel is latency-
-// not math-bound (ncu r1a: 15 us per CTA for ~3 us of MMA), so prefetch depth and CTAs/SM (3-4, was 2) are what
-// count.  The MMAs are mma.sync (1.9 % + 1.9 % of FLOPs at 3 s); moving S and O into TMEM with tcgen05 is the
+// and issue-bound, not math-bound (ncu r1a: 15 us per CTA for ~3 us of MMA), so prefetch depth, CTAs/SM (4, was
+// 2) and instructions per score element are what count: the bias add has three tile-level fast paths (table
+// index never clamps / always clamps high / always clamps low) that need no per-element index arithmetic.  The MMAs are mma.sync (1.9 % + 1.9 % of FLOPs at 3 s); moving S and O into TMEM with tcgen05 is the
 // planned next step for the long-context configs.
 #include <cuda_fp16.h>
 
@@ -31,8 +34,9 @@ constexpr int ARING = 5;     // ring depth (prefetch distance 4 tiles)
 constexpr int TILE_ELEMS = AT * ALD;
 constexpr int QKV_LD = 3 * kHidden;
 
+constexpr int QT_PAD = 24;   // slack columns: rows past T index up to 15 columns beyond the computed range
 __host__ __device__ constexpr int attn_smem_bytes(int qt_cols) {
-    return AQ * ALD * 2 + ARING * TILE_ELEMS * 2 + AQ * (qt_cols + 8) * 2;
+    return ARING * TILE_ELEMS * 2 + AQ * (qt_cols + QT_PAD) * 2;
 }
 
 // copy 32 rows x 64 bf16 from global (row stride ld) into a padded smem tile; rows >= valid are zero-filled
@@ -53,10 +57,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
     if (i0 >= T) return;
     const int head = blockIdx.y;
     extern __shared__ __align__(16) uint8_t smem[];
-    bf16* sq = reinterpret_cast<bf16*>(smem);
-    bf16* ring = sq + AQ * ALD;
+    bf16* ring = reinterpret_cast<bf16*>(smem);
     __half* sqt = reinterpret_cast<__half*>(ring + ARING * TILE_ELEMS);
-    const int qt_ld = qt_cols + 8;
+    const int qt_ld = qt_cols + QT_PAD;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gq = lane >> 2, tq = lane & 3;
 
@@ -66,6 +69,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
 
     // table columns this tile can reach: rel = i - j, i in [i0, min(i0+63, T-1)], j in [0, T-1]
     const int i_hi = min(i0 + AQ - 1, T - 1);
+    const bool warp_active = i0 + warp * 16 < T;     // warps whose 16 rows are all past T only help with the loads
     const int c_lo = max(i0 - (T - 1), -kMaxRel) + kMaxRel;
     const int c_hi = min(i_hi, kMaxRel - 1) + kMaxRel;
     const int chunk_lo = c_lo / AT;
@@ -88,18 +92,23 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
         cp_async_commit();
     };
 
-    // prologue: Q tile rides in the first group
-    for (int i = tid; i < AQ * 8; i += 128) {
-        const int r = i >> 3, c = i & 7;
-        const bool ok = r < T - i0;
-        cp_async_16(smem_u32(sq + r * ALD + c * 8), q_g + (int64_t)(ok ? r : 0) * QKV_LD + c * 8, ok);
+    // Q fragments straight from global (read once): a0 = (row g, dims 2t..2t+1), a1 = row g+8, a2/a3 = dims +8
+    uint32_t qf[4][4];
+    {
+        const int r0 = i0 + warp * 16 + gq, r1 = r0 + 8;
+        const bf16* p0 = q_g + (int64_t)(warp * 16 + gq) * QKV_LD + tq * 2;
+        const bf16* p1 = p0 + 8 * QKV_LD;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            qf[ks][0] = r0 < T ? __ldg(reinterpret_cast<const uint32_t*>(p0 + ks * 16)) : 0u;
+            qf[ks][1] = r1 < T ? __ldg(reinterpret_cast<const uint32_t*>(p1 + ks * 16)) : 0u;
+            qf[ks][2] = r0 < T ? __ldg(reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 8)) : 0u;
+            qf[ks][3] = r1 < T ? __ldg(reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 8)) : 0u;
+        }
     }
 #pragma unroll
     for (int s = 0; s < ARING - 1; ++s) issue(s);
 
-    uint32_t qf[4][4];  // Q fragments for the 4 k-steps (dims 0..63), reused by every tile
-    const int a_row = warp * 16 + (lane & 15);
-    const int a_col = (lane >> 4) * 8;
     const int b_row = (lane & 7) + ((lane >> 4) << 3);
     const int b_col = ((lane >> 3) & 1) * 8;
 
@@ -111,19 +120,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
     float row_max[2] = {-INFINITY, -INFINITY};
     float row_sum[2] = {0.f, 0.f};
     uint32_t pf[2][4];  // P as A-operand fragments for the two 16-key k-steps of the current key tile
-    const int qi[2] = {min(i0 + warp * 16 + gq, T - 1), min(i0 + warp * 16 + gq + 8, T - 1)};  // clamped: rows >= T are never stored
+    const int qi[2] = {i0 + warp * 16 + gq, i0 + warp * 16 + gq + 8};
     const __half* qt_row[2] = {sqt + (warp * 16 + gq) * qt_ld, sqt + (warp * 16 + gq + 8) * qt_ld};
-    constexpr float kLog2e = 1.4426950408889634f;
 
     for (int s = 0; s < n_tiles; ++s) {
         cp_async_wait<ARING - 2>();
         __syncthreads();            // tile s has landed for everyone; everyone is done with tile s-1
         issue(s + ARING - 1);       // refill the slot tile s-1 occupied
         const bf16* tile = ring + (s % ARING) * TILE_ELEMS;
-        if (s == 0) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qf[ks], smem_u32(sq + a_row * ALD + ks * 16 + a_col));
-        }
+        if (!warp_active) continue;
         if (s < n_pe) {
             // ---- QT[:, chunk] = Q . pe_k[chunk]^T  (16 x 32 per warp), stored as fp16 ----------------------
 #pragma unroll
@@ -144,7 +149,6 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
                 *reinterpret_cast<__half2*>(r0 + 8) = __floats2half2_rn(c1[0], c1[1]);
                 *reinterpret_cast<__half2*>(r1 + 8) = __floats2half2_rn(c1[2], c1[3]);
             }
-            if (s == n_pe - 1) __syncwarp();   // a warp reads back only the QT rows it wrote itself
         } else if (((s - n_pe) & 1) == 0) {
             // ---- key tile: S = Q K^T (+ bias), online softmax, P fragments ------------------------------
             const int j0 = ((s - n_pe) >> 1) * AT;
@@ -164,20 +168,56 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
                     mma_16816(sc[np * 2 + 1], qf[ks], b1);
                 }
             }
-            float mx[2] = {row_max[0], row_max[1]};
+            // ---- + relative-position bias: rel = i - j over this warp's 16 rows x the tile's 32 keys -----------
+            const int rel_max = i0 + warp * 16 + 15 - j0;
+            const int rel_min = i0 + warp * 16 - (j0 + AT - 1);
+            if (rel_max < kMaxRel && rel_min >= -kMaxRel) {
+                // no clamping anywhere in the tile: column = (i - j) + 160, constant offsets from a per-row base
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
+                for (int r = 0; r < 2; ++r) {
+                    const __half* base = qt_row[r] + (qi[r] - j0 - tq * 2 + kMaxRel - cbase);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int r = e >> 1;
-                    const int j = j0 + n * 8 + tq * 2 + (e & 1);
-                    int rel = qi[r] - j;
-                    rel = max(-kMaxRel, min(kMaxRel - 1, rel)) + kMaxRel - cbase;
-                    const float v = j < T ? (sc[n][e] + __half2float(qt_row[r][rel])) * kLog2e : -INFINITY;
-                    sc[n][e] = v;
-                    mx[r] = fmaxf(mx[r], v);
+                    for (int n = 0; n < 4; ++n) {
+                        sc[n][r * 2 + 0] += __half2float(base[-n * 8]);
+                        sc[n][r * 2 + 1] += __half2float(base[-n * 8 - 1]);
+                    }
+                }
+            } else if (rel_min >= kMaxRel - 1 || rel_max <= -kMaxRel) {
+                // every pair clamps to the same table edge: one scalar per query row
+                const int col = (rel_min >= kMaxRel - 1 ? kRelCols - 1 : 0) - cbase;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float bias = __half2float(qt_row[r][col]);
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) {
+                        sc[n][r * 2 + 0] += bias;
+                        sc[n][r * 2 + 1] += bias;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int r = e >> 1;
+                        int rel = min(qi[r], T - 1) - (j0 + n * 8 + tq * 2 + (e & 1));
+                        rel = max(-kMaxRel, min(kMaxRel - 1, rel)) + kMaxRel - cbase;
+                        sc[n][e] += __half2float(qt_row[r][rel]);
+                    }
                 }
             }
+            if (j0 + AT > T) {   // ragged last tile: keys >= T do not exist
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (j0 + n * 8 + tq * 2 + (e & 1) >= T) sc[n][e] = -INFINITY;
+            }
+            float mx[2] = {row_max[0], row_max[1]};
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], sc[n][e]);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
@@ -226,6 +266,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
     }
 
     // ---- epilogue ---------------------------------------------------------------------------------
+    if (!warp_active) return;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         float l = row_sum[r];

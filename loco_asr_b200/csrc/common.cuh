@@ -130,6 +130,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* desc,
         : "memory");
 }
 
+// 1-D bulk copy global -> shared through the TMA engine (no tensor map), completion on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -168,6 +175,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Wait for the outstanding tcgen05.ld's, then pin `r` behind the wait: the empty volatile asm statements give the
 // compiler a data dependency it cannot hoist above the wait (the loads write the registers asynchronously).
@@ -188,6 +204,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;       // SBO
     d |= (uint64_t)1 << 46;                 // version
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// Same descriptor family without swizzle (layout type 0), K-major: 8-row x 16-byte core matrices; rows of a core
+// matrix 16 B apart, 8-row groups `sbo` bytes apart, the two 8-element K halves of one MMA `lbo` bytes apart
+// (canonical layout ((8,m),(8,2)):((16B,SBO),(2B,LBO)), cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::K>).
+__device__ __forceinline__ uint64_t umma_desc_noswizzle_kmajor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;                 // version
     return d;
 }
 // Instruction descriptor, kind::f16: bf16 A/B (format 1), fp32 accumulate, both operands K-major.

@@ -50,6 +50,7 @@ struct UttMeta {          // per-utterance geometry, device-resident
     int32_t out_row;      // first row in the compact hidden_out buffer (prefix sum of t6)
 };
 
+int frontend_init();
 int wave_stats_chunks(int max_t0);
 int launch_wave_stats(const float* wave, const UttMeta* meta, int n_utts, int chunks, const float* w0 /*[512,10]*/,
                       const float* gn_w, const float* gn_b, double* partial /*[n, chunks, 65]*/, float* scale /*[n,512]*/,
@@ -69,7 +70,19 @@ int launch_final_ln_pool(const bf16* x, const float* gamma, const float* beta, c
 // row_frame[r] = frame index of row r inside its utterance, or -1 for slot padding rows.
 int launch_row_frames(const UttMeta* meta, int n_utts, int max_slot6, int32_t* row_frame, cudaStream_t s);
 
-// ---- positional conv (posconv.cu) --------------------------------------------------------------
+// ---- positional conv on tcgen05 (posconv_tc.cu) ------------------------------------------------
+struct PcTile {      // one 128-frame output tile of one utterance
+    int32_t row0;    // row of the tile's first frame in the [R6, 768] buffers
+    int32_t f0;      // that frame's index inside its utterance
+    int32_t t6;      // the utterance's frame count
+    int32_t pad_;
+};
+int posconv_tc_init();
+// w_tc: [16 groups][128 taps][6 in-chunks][48 out][8 in] bf16 -- one tap's block is a ready-made UMMA B operand.
+int launch_posconv_tc(const bf16* h, const bf16* w_tc, const float* bias, const PcTile* tiles, int n_tiles, bf16* pc,
+                      cudaStream_t s);
+
+// ---- positional conv, mma.sync debug cross-check (posconv.cu) ----------------------------------
 // pc[r, :] = gelu(bias + grouped_conv(h)[r, :]) with zero padding at each utterance's own boundaries.
 int posconv_init();
 int launch_posconv(const bf16* h, const bf16* w /*[16][128][48 out][48 in]*/, const float* bias, const UttMeta* meta,
