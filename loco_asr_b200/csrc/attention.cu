@@ -12,8 +12,8 @@
 // score matrix never exists: an online softmax runs in registers while keys / values stream by.
 //
 // Variable-length utterances: one CTA per (64-query tile, head, utterance); no padding, no mask tensor.
-// Everything the CTA consumes (needed pe_k chunks, then K and V tiles) is ONE stream of 32-row x 64 tiles pulled
-// through a 5-deep cp.async ring with a single __syncthreads per tile; at 3 s utterances the kernel is latency-
+// Everything the CTA consumes (needed pe_k tiles of 64 table rows, then 32-key K|V tiles) is ONE stream of 9 KB
+// tiles pulled through a 4-deep cp.async ring with a single __syncthreads per tile; at 3 s utterances the kernel is latency-
 // and issue-bound, not math-bound (ncu r1a: 15 us per CTA for ~3 us of MMA), so prefetch depth, CTAs/SM (4, was
 // 2) and instructions per score element are what count: the bias add has three tile-level fast paths (table
 // index never clamps / always clamps high / always clamps low) that need no per-element index arithmetic.  The MMAs are mma.sync (1.9 % + 1.9 % of FLOPs at 3 s); moving S and O into TMEM with tcgen05 is the
@@ -28,10 +28,11 @@ namespace loco {
 namespace {
 
 constexpr int AQ = 64;       // queries per CTA (16 per warp)
-constexpr int AT = 32;       // rows per streamed tile (pe_k rows, keys, or values)
+constexpr int AT = 32;       // keys per streamed K|V tile
+constexpr int APE = 64;      // pe_k rows per streamed table tile
 constexpr int ALD = 72;      // padded bf16 row length (144 B: conflict-free ldmatrix)
-constexpr int ARING = 5;     // ring depth (prefetch distance 4 tiles)
-constexpr int TILE_ELEMS = AT * ALD;
+constexpr int ARING = 4;     // ring depth (prefetch distance 3 tiles)
+constexpr int TILE_ELEMS = 64 * ALD;   // a ring slot holds 64 rows: one pe_k tile, or 32 keys followed by their 32 values
 constexpr int QKV_LD = 3 * kHidden;
 
 constexpr int QT_PAD = 24;   // slack columns: rows past T index up to 15 columns beyond the computed range
@@ -42,7 +43,7 @@ __host__ __device__ constexpr int attn_smem_bytes(int qt_cols) {
 // copy 32 rows x 64 bf16 from global (row stride ld) into a padded smem tile; rows >= valid are zero-filled
 __device__ __forceinline__ void load_tile32(bf16* dst, const bf16* src, int64_t ld, int valid, int tid) {
 #pragma unroll
-    for (int i = tid; i < AT * 8; i += 128) {
+    for (int i = tid; i < 32 * 8; i += 128) {
         const int r = i >> 3, c = i & 7;
         const bool ok = r < valid;
         cp_async_16(smem_u32(dst + r * ALD + c * 8), src + (int64_t)(ok ? r : 0) * ld + c * 8, ok);
@@ -72,21 +73,26 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
     const bool warp_active = i0 + warp * 16 < T;     // warps whose 16 rows are all past T only help with the loads
     const int c_lo = max(i0 - (T - 1), -kMaxRel) + kMaxRel;
     const int c_hi = min(i_hi, kMaxRel - 1) + kMaxRel;
-    const int chunk_lo = c_lo / AT;
-    const int n_pe = c_hi / AT - chunk_lo + 1;   // <= qt_cols / 32 by construction of qt_cols on the host
-    const int cbase = chunk_lo * AT;
+    const int chunk_lo = c_lo / APE;
+    const int n_pe = c_hi / APE - chunk_lo + 1;
+    const int cbase = (c_lo / 16) * 16;          // QT column 0; c_hi - cbase < qt_cols by construction on the host
     const int n_kv = (T + AT - 1) / AT;
-    const int n_tiles = n_pe + 2 * n_kv;         // stream: pe chunks, then K0 V0 K1 V1 ...
+    const int n_tiles = n_pe + n_kv;             // stream: pe_k tiles, then K0|V0, K1|V1, ...
+    // table columns THIS WARP's 16 rows can reach (a subset of the CTA's): n-tile pairs outside it are skipped
+    const int cw_lo = max(i0 + warp * 16 - (T - 1), -kMaxRel) + kMaxRel;
+    const int cw_hi = min(min(i0 + warp * 16 + 15, T - 1), kMaxRel - 1) + kMaxRel;
 
     auto issue = [&](int s) {
         if (s < n_tiles) {
             bf16* dst = ring + (s % ARING) * TILE_ELEMS;
             if (s < n_pe) {
-                load_tile32(dst, pe_k + (int64_t)(chunk_lo + s) * AT * kHeadDim, kHeadDim, AT, tid);
+                const bf16* src = pe_k + (int64_t)(chunk_lo + s) * APE * kHeadDim;
+                load_tile32(dst, src, kHeadDim, 32, tid);
+                load_tile32(dst + 32 * ALD, src + 32 * kHeadDim, kHeadDim, 32, tid);
             } else {
-                const int kv = (s - n_pe) >> 1;
-                const bf16* src = ((s - n_pe) & 1) ? v_g : k_g;
-                load_tile32(dst, src + (int64_t)kv * AT * QKV_LD, QKV_LD, T - kv * AT, tid);
+                const int kv = s - n_pe;
+                load_tile32(dst, k_g + (int64_t)kv * AT * QKV_LD, QKV_LD, T - kv * AT, tid);
+                load_tile32(dst + 32 * ALD, v_g + (int64_t)kv * AT * QKV_LD, QKV_LD, T - kv * AT, tid);
             }
         }
         cp_async_commit();
@@ -130,9 +136,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
         const bf16* tile = ring + (s % ARING) * TILE_ELEMS;
         if (!warp_active) continue;
         if (s < n_pe) {
-            // ---- QT[:, chunk] = Q . pe_k[chunk]^T  (16 x 32 per warp), stored as fp16 ----------------------
+            // ---- QT[:, tile] = Q . pe_k[tile]^T  (16 x 64 per warp), stored as fp16 ------------------------
 #pragma unroll
-            for (int np = 0; np < 2; ++np) {
+            for (int np = 0; np < 4; ++np) {
+                const int c16 = (chunk_lo + s) * APE + np * 16;
+                if (c16 + 15 < cw_lo || c16 > cw_hi) continue;   // warp-uniform
                 float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
@@ -142,16 +150,16 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
                     mma_16816(c0, qf[ks], b0);
                     mma_16816(c1, qf[ks], b1);
                 }
-                __half* r0 = sqt + (warp * 16 + gq) * qt_ld + s * AT + np * 16 + tq * 2;
+                __half* r0 = sqt + (warp * 16 + gq) * qt_ld + (c16 - cbase) + tq * 2;
                 __half* r1 = r0 + 8 * qt_ld;
                 *reinterpret_cast<__half2*>(r0) = __floats2half2_rn(c0[0], c0[1]);
                 *reinterpret_cast<__half2*>(r1) = __floats2half2_rn(c0[2], c0[3]);
                 *reinterpret_cast<__half2*>(r0 + 8) = __floats2half2_rn(c1[0], c1[1]);
                 *reinterpret_cast<__half2*>(r1 + 8) = __floats2half2_rn(c1[2], c1[3]);
             }
-        } else if (((s - n_pe) & 1) == 0) {
-            // ---- key tile: S = Q K^T (+ bias), online softmax, P fragments ------------------------------
-            const int j0 = ((s - n_pe) >> 1) * AT;
+        } else {
+            // ---- K|V tile: S = Q K^T (+ bias), online softmax, O += P V ----------------------------------
+            const int j0 = (s - n_pe) * AT;
             float sc[4][4];
 #pragma unroll
             for (int n = 0; n < 4; ++n)
@@ -247,8 +255,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
                 o[n][0] *= corr[0]; o[n][1] *= corr[0];
                 o[n][2] *= corr[1]; o[n][3] *= corr[1];
             }
-        } else {
-            // ---- value tile: O += P V ([key][dim] storage; ldmatrix.trans yields the (k = key, n = dim) operand)
+            // O += P V ([key][dim] storage; ldmatrix.trans yields the (k = key, n = dim) operand)
+            const bf16* vt = tile + 32 * ALD;
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
                     uint32_t b[4];
                     const int key = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                     const int dim = dp * 16 + (lane >> 4) * 8;
-                    ldmatrix_x4_trans(b, smem_u32(tile + key * ALD + dim));
+                    ldmatrix_x4_trans(b, smem_u32(vt + key * ALD + dim));
                     const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
                     mma_16816(o[dp * 2], pf[kk], b0);
                     mma_16816(o[dp * 2 + 1], pf[kk], b1);
@@ -282,13 +290,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
     }
 }
 
-// columns of the bias table a 64-query tile can need when no utterance in the batch exceeds max_t6 frames
+// columns of the bias table a 64-query tile can need when no utterance in the batch exceeds max_t6 frames:
+// c_hi - c_lo <= T + 62, plus up to 15 for aligning column 0 down to a multiple of 16
 int qt_cols_for(int max_t6) {
-    int width = max_t6 + AQ - 1;
-    if (width > kRelCols) width = kRelCols;
-    int chunks = (width - 1 + AT - 1) / AT + 1;   // worst-case alignment of [c_lo, c_hi] against 32-column chunks
-    if (chunks > kRelCols / AT) chunks = kRelCols / AT;
-    return chunks * AT;
+    int cols = (max_t6 + 62 + 16 + 15) / 16 * 16;
+    return cols > kRelCols ? kRelCols : cols;
 }
 
 }  // namespace
