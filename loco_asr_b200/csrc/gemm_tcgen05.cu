@@ -1,5 +1,6 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma with
-// the fp32 accumulator in TMEM -> tcgen05.ld epilogue (bias / exact GELU / residual) -> bf16 global stores.
+// the fp32 accumulator in TMEM -> tcgen05.ld epilogue (bias / exact GELU / residual) -> swizzled smem panel ->
+// TMA store (the residual operand arrives through the same panel by TMA load).
 //
 // One kernel covers every GEMM-shaped stage of the encoder:
 //   a3  conv layers 1-6 as implicit GEMM (A rows overlap: lda = 2*512, K = k*512)   HF modeling_speecht5.py:210-228
@@ -12,7 +13,10 @@
 // warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator, warps 4-11 = epilogue: warp w owns TMEM lanes
 // 32*(w%4)..+31 (one accumulator row per thread) and column half (w-4)/4, i.e. two warps per SM sub-partition so
 // the epilogue's dependent FP32/MUFU chains overlap (with one warp per sub-partition the GELU epilogue, not
-// the MMA, set the pace: ncu r1a, tensor pipe 14 % active on FFN1).
+// the MMA, set the pace: ncu r1a, tensor pipe 14 % active on FFN1).  Each epilogue warp owns a 4 KB SWIZZLE_128B
+// staging panel (32 rows x 64 columns): with one accumulator row per thread, direct global stores / residual loads
+// touch 32 different 128-byte lines per instruction and made the K = 768 GEMMs LSU-bound (out_proj 48 % of peak);
+// through the panel every global access is a full-line TMA transfer and the M tail is clipped by the tensor map.
 #include <stdio.h>
 
 #include "common.cuh"
@@ -33,24 +37,27 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int PANEL_BYTES = 32 * 128;       // one epilogue warp's staging panel: 32 rows x 64 bf16
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * PANEL_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct __align__(8) Barriers {
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
     uint64_t tmem_full[ACC_STAGES];
     uint64_t tmem_empty[ACC_STAGES];
+    uint64_t res_full[NUM_EPI_WARPS];   // residual panel landed (one per epilogue warp)
     uint32_t tmem_base;
 };
 
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, bf16* __restrict__ C,
-               int64_t ldc, const float* __restrict__ bias, const bf16* __restrict__ R, int64_t ldr, int M, int N, int K) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
+               const float* __restrict__ bias, int M, int N, int K) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-    Barriers* bars = reinterpret_cast<Barriers*>(smem_aligned + STAGES * STAGE_BYTES);
+    Barriers* bars = reinterpret_cast<Barriers*>(smem_aligned + STAGES * STAGE_BYTES + NUM_EPI_WARPS * PANEL_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -62,6 +69,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        tma_prefetch_desc(&tma_c);
+        if (EPI == EPI_BIAS_RESIDUAL) tma_prefetch_desc(&tma_r);
+        for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(smem_u32(&bars->res_full[w]), 1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&bars->full[s]), 1);
             mbar_init(smem_u32(&bars->empty[s]), 1);
@@ -129,68 +139,89 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: TMEM -> registers -> global =====================
+        // ===================== epilogue: TMEM -> registers -> swizzled smem panel -> TMA store ==============
         const int q = warp & 3;             // TMEM lane quadrant this warp may access
         const int half = (warp - 4) >> 2;   // which 128 of the tile's 256 columns
-        constexpr int CHUNKS = BN / 32 / 2; // 32-column chunks per warp
+        const uint32_t panel = smem_base + STAGES * STAGE_BYTES + (warp - 4) * PANEL_BYTES;
+        const uint32_t my_row = panel + lane * 128;      // this thread's accumulator row inside the panel
+        const uint32_t res_bar = smem_u32(&bars->res_full[warp - 4]);
+        uint32_t res_phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles_n) * BM;
+            const int m0 = (tile / n_tiles_n) * BM + q * 32;
             const int n0 = (tile % n_tiles_n) * BN + half * (BN / 2);
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < M;
             mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
-            bf16* c_row = C + (int64_t)row * ldc + n0;
-            const bf16* r_row = (EPI == EPI_BIAS_RESIDUAL) ? (R + (int64_t)row * ldr + n0) : nullptr;
             uint32_t v[2][32];
             tmem_ld_32x32(t_row, v[0]);
 #pragma unroll
-            for (int c = 0; c < CHUNKS; ++c) {
+            for (int c = 0; c < 4; ++c) {           // 4 chunks of 32 columns = 2 panels of 64
+                if ((c & 1) == 0) {
+                    // the previous TMA store must have finished reading the panel before it is overwritten
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                    if (EPI == EPI_BIAS_RESIDUAL && lane == 0) {
+                        mbar_arrive_expect_tx(res_bar, PANEL_BYTES);
+                        tma_load_2d(panel, &tma_r, res_bar, n0 + (c >> 1) * 64, m0);
+                    }
+                }
                 tmem_ld_wait(v[c & 1]);
-                if (c + 1 < CHUNKS) {
+                if (c + 1 < 4) {
                     tmem_ld_32x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);   // next chunk in flight during the math
                 } else {
                     // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
                 }
-                if (row_ok) {
+                if (EPI == EPI_BIAS_RESIDUAL && (c & 1) == 0) {
+                    mbar_wait(res_bar, res_phase);
+                    res_phase ^= 1u;
+                }
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float f[8];
+                for (int j = 0; j < 32; j += 8) {
+                    float f[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c & 1][j + e]);
-                        if (bias != nullptr) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j + 4));
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                        }
-                        if (EPI == EPI_BIAS_GELU) {
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c & 1][j + e]);
+                    if (bias != nullptr) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j + 4));
+                        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                    }
+                    if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
-                        }
-                        if (EPI == EPI_BIAS_RESIDUAL) {
-                            const uint4 rr = __ldg(reinterpret_cast<const uint4*>(r_row + c * 32 + j));
-                            const float2 r0 = unpack_bf16(rr.x), r1 = unpack_bf16(rr.y), r2 = unpack_bf16(rr.z),
-                                         r3 = unpack_bf16(rr.w);
-                            f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
-                            f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
-                        }
-                        uint4 o;
-                        o.x = pack_bf16(f[0], f[1]);
-                        o.y = pack_bf16(f[2], f[3]);
-                        o.z = pack_bf16(f[4], f[5]);
-                        o.w = pack_bf16(f[6], f[7]);
-                        *reinterpret_cast<uint4*>(c_row + c * 32 + j) = o;
+                        for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+                    }
+                    // 16-byte chunk k of row r sits at r*128 + ((k ^ (r & 7)) * 16) under SWIZZLE_128B
+                    const uint32_t addr = my_row + ((((c & 1) * 4 + (j >> 3)) ^ (lane & 7)) << 4);
+                    if (EPI == EPI_BIAS_RESIDUAL) {
+                        const uint4 rr = lds128(addr);
+                        const float2 r0 = unpack_bf16(rr.x), r1 = unpack_bf16(rr.y), r2 = unpack_bf16(rr.z),
+                                     r3 = unpack_bf16(rr.w);
+                        f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+                        f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+                    }
+                    uint4 o;
+                    o.x = pack_bf16(f[0], f[1]);
+                    o.y = pack_bf16(f[2], f[3]);
+                    o.z = pack_bf16(f[4], f[5]);
+                    o.w = pack_bf16(f[6], f[7]);
+                    sts128(addr, o);
+                }
+                if (c & 1) {
+                    fence_proxy_async_smem();       // generic-proxy panel writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tma_c, panel, n0 + (c >> 1) * 64, m0);
+                        bulk_commit();
                     }
                 }
             }
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
+        if (lane == 0) bulk_wait<0>();   // all of this warp's stores have landed before the CTA retires
     }
 
     tc_fence_before();
@@ -218,8 +249,9 @@ int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, 
 }
 
 template <int EPI>
-int launch_t(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int grid, cudaStream_t stream) {
-    gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, g.C, g.ldc, g.bias, g.R, g.ldr, g.M, g.N, g.K);
+int launch_t(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr,
+             int grid, cudaStream_t stream) {
+    gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mc, mr, g.bias, g.M, g.N, g.K);
     return (int)cudaGetLastError();
 }
 
@@ -253,12 +285,20 @@ int gemm_tc_launch(const GemmArgs& g, int num_sms, cudaStream_t stream) {
     if (rc) return rc;
     rc = make_map(&mb, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K, BN);
     if (rc) return rc;
+    CUtensorMap mc, mr;
+    rc = make_map(&mc, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc, 32);
+    if (rc) return rc;
+    mr = mc;
+    if (g.epilogue == EPI_BIAS_RESIDUAL) {
+        rc = make_map(&mr, g.R, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldr, 32);
+        if (rc) return rc;
+    }
     const int n_tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
     switch (g.epilogue) {
-        case EPI_BIAS: return launch_t<EPI_BIAS>(g, ma, mb, grid, stream);
-        case EPI_BIAS_GELU: return launch_t<EPI_BIAS_GELU>(g, ma, mb, grid, stream);
-        case EPI_BIAS_RESIDUAL: return launch_t<EPI_BIAS_RESIDUAL>(g, ma, mb, grid, stream);
+        case EPI_BIAS: return launch_t<EPI_BIAS>(g, ma, mb, mc, mr, grid, stream);
+        case EPI_BIAS_GELU: return launch_t<EPI_BIAS_GELU>(g, ma, mb, mc, mr, grid, stream);
+        case EPI_BIAS_RESIDUAL: return launch_t<EPI_BIAS_RESIDUAL>(g, ma, mb, mc, mr, grid, stream);
     }
     return (int)cudaErrorInvalidValue;
 }
