@@ -182,3 +182,38 @@ def test_linearity_property_of_prenet_scale(encoder):
     w = synth_wave(40000, 30, 0, kind="noise")
     p, _, _ = H.run_encoder(encoder, [w, (w * 8).astype(np.float32)])
     assert H.cosine(p[0], p[1]) > 0.9995
+
+
+def test_extract_cli_writes_reference_format_and_head_argmax_matches(tmp_path, capsys):
+    """BASELINE.json configs[4] in miniature: the drop-in CLI on synthetic SLURP-shaped utterances -> pickles the
+    reference's dataset class can read; the intent head's argmax on them equals the head on the CPU oracle."""
+    import pickle
+    from loco_asr_b200 import extract
+    from loco_asr_b200.head import IntentHead
+    from loco_asr_b200.synth import slurp_shaped_lengths, synth_state_dict
+    n = 12
+    extract.main(["-m", "audio", "-s", "test", "--synthetic", str(n), "--out-root", str(tmp_path)])
+    folder = extract.output_folder(str(tmp_path), "base", "test", "audio")
+    files = sorted(os.listdir(folder))
+    assert len(files) == n and all(f.endswith("_embedding_and_target.pickle") for f in files)
+    sd = synth_state_dict(seed=1)
+    lens = slurp_shaped_lengths(n, 1234)
+    w, b = synth_head(3)
+    head = IntentHead(w, b)
+    for i in (0, 5, 11):
+        with open(extract.output_path(folder, f"synth{i}"), "rb") as fh:
+            d = pickle.load(fh)
+        assert d["id"] == f"synth{i}" and d["embedding"].dtype == np.float32 and d["embedding"].shape == (1, 768)
+        assert d["target"].shape == (101,) and d["target"].sum() == 1
+        ref = O.encode_utterance(sd, torch.from_numpy(synth_wave(int(lens[i]), 1234, i))).mean(0)
+        got = torch.from_numpy(d["embedding"])[0]
+        assert H.cosine(got, ref) >= COS_MIN
+        assert int(head.predict(got[None])) == int(head.predict(ref[None]))
+    # resume: nothing left to do
+    extract.main(["-m", "audio", "-s", "test", "--synthetic", str(n), "--out-root", str(tmp_path)])
+    assert "wrote 0 files" in capsys.readouterr().out
+    # the reference's [T, 768] layout on request
+    extract.main(["-m", "audio", "-s", "devel", "--synthetic", "3", "--out-root", str(tmp_path), "--full-sequence"])
+    with open(extract.output_path(extract.output_folder(str(tmp_path), "base", "devel", "audio"), "synth1"), "rb") as fh:
+        d = pickle.load(fh)
+    assert d["embedding"].shape == (O.frame_lengths(int(slurp_shaped_lengths(3, 1234)[1]))[-1], 768)
