@@ -45,6 +45,9 @@ def parse_args():
     p.add_argument("--cpu-sample", type=int, default=96, help="utterances in the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--seed", type=int, default=1234)
+    p.add_argument("--attn-impl", type=int, default=-1, help="debug: force attention kernel (0 tcgen05, 1 mma.sync)")
+    p.add_argument("--workload", choices=["slurp", "long30", "long60"], default="slurp",
+                   help="slurp = BASELINE configs[1] (the metric's workload); long30/long60 = configs[3] (256 x 30 s / 128 x 60 s)")
     return p.parse_args()
 
 
@@ -169,7 +172,14 @@ def main():
     import torch.distributed as dist
 
     enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device=dev)
-    lengths = slurp_shaped_lengths(args.utts, args.seed + rank)          # every rank owns a full set (weak scaling)
+    if args.attn_impl >= 0:
+        enc.debug_set("attn_impl", args.attn_impl)
+    if args.workload == "slurp":
+        lengths = slurp_shaped_lengths(args.utts, args.seed + rank)      # every rank owns a full set (weak scaling)
+    else:
+        n_long, sec = (256, 30) if args.workload == "long30" else (128, 60)
+        lengths = np.full(n_long, sec * 16000, dtype=np.int64)
+        args.utts = n_long
     batches = make_batches(lengths, max_frames=args.max_frames)
     nb = len(batches)
     order = interleaved_order(nb)
@@ -313,7 +323,9 @@ def main():
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(n=args.utts), "utterances_per_gpu": int(args.utts), "batches": nb,
+            "config": {"workload": WORKLOAD.format(n=args.utts) if args.workload == "slurp" else
+                       f"SpeechT5-base speech encoder, long-context segments (BASELINE.json configs[3]): {args.utts} x {int(lengths[0]) // 16000} s",
+                       "utterances_per_gpu": int(args.utts), "batches": nb,
                        "max_frames_per_batch": args.max_frames, "audio_s_per_step": timed_audio / K / max(world, 1),
                        "weights": "random-init SpeechT5-base (seed 1)", "accumulate": "fp32",
                        "l2": "inputs larger than L2 (per-step working set ~10 GB)",

@@ -76,6 +76,9 @@ struct loco_handle {
     // debug
     int gemm_impl = 0;
     int posconv_impl = 0;
+    int attn_impl = -1;         // -1 = by length (tcgen05 from attn_tc_min_frames), 0 = tcgen05, 1 = mma.sync
+    int attn_tc_min_frames = 1024;
+    alignas(64) CUtensorMap pe_map;   // pe_k [320, 64] for the tcgen05 attention kernel
     int stop_after_layer = -1;
     Layout last;
     void* last_ws = nullptr;
@@ -427,6 +430,7 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
     h->num_sms = prop.multiProcessorCount;
     int rc = gemm_tc_init();
     if (!rc) rc = attention_init();
+    if (!rc) rc = attention_tc_init();
     if (!rc) rc = posconv_init();
     if (!rc) rc = posconv_tc_init();
     if (!rc) rc = frontend_init();
@@ -526,6 +530,8 @@ int loco_finalize_weights(loco_handle* h) {
     if ((rc = upload_f32(h, "wrapped_encoder.layer_norm.weight", {768}, &h->eln_w))) return rc;
     if ((rc = upload_f32(h, "wrapped_encoder.layer_norm.bias", {768}, &h->eln_b))) return rc;
     if ((rc = upload_bf16(h, "wrapped_encoder.embed_positions.pe_k.weight", {320, 64}, &h->pe_k))) return rc;
+    if (make_tensor_map_bf16_sw128(&h->pe_map, h->pe_k, 64, 320, 64, 160))
+        return fail(h, LOCO_ERR_CUDA, "cuTensorMapEncodeTiled failed for pe_k");
     h->layers.resize(h->cfg.encoder_layers);
     for (int l = 0; l < h->cfg.encoder_layers; ++l) {
         const std::string p = "wrapped_encoder.layers." + std::to_string(l) + ".";
@@ -627,6 +633,12 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         CK(cudaMemsetAsync(ws + b.off + (size_t)b.rows * kConvDim * 2, 0, (size_t)8 * kConvDim * 2, s));
     }
     LAUNCH(CAT_ROWOPS, launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
+    // slot padding rows of ctx are never written by the attention kernels; keep them finite (zero) so they stay finite
+    // through every later layer -- the tcgen05 attention multiplies masked (P = 0) key rows into O, and 0 * NaN = NaN
+    CK(cudaMemsetAsync(ws + L.bufs["ctx"].off, 0, (size_t)L.R6 * kHidden * sizeof(bf16), s));
+    alignas(64) CUtensorMap qkv_map;
+    if (make_tensor_map_bf16_sw128(&qkv_map, B("qkv"), 3 * kHidden, (uint64_t)L.R6, 3 * kHidden, 128))
+        return fail(h, LOCO_ERR_CUDA, "cuTensorMapEncodeTiled failed for qkv");
 
     // ---- conv feature encoder -----------------------------------------------------------------------
     LAUNCH(CAT_FRONTEND, launch_wave_stats(wave_dev, meta, n_utts, L.chunks, h->w0, h->gn_w, h->gn_b, partial, scale, shift, s), 2);
@@ -672,7 +684,12 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         g.A = B("x"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wqkv; g.C = B("qkv"); g.ldc = 3 * kHidden;
         g.bias = w.bqkv; g.M = R6; g.N = 3 * kHidden; g.K = kHidden; g.epilogue = EPI_BIAS;
         if ((rc = run_gemm(h, g, s))) return rc;
-        LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, n_utts, L.max_t6, B("ctx"), s), 1);
+        // both kernels are product paths, chosen by shape: the mma.sync kernel wins on short utterances (64-row tiles, 3-4
+        // CTAs/SM), the tcgen05 kernel on long ones (128 x 128 blocks, MMA off the issue slots)
+        if (h->attn_impl == 1 || (h->attn_impl < 0 && L.max_t6 < h->attn_tc_min_frames))
+            LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, n_utts, L.max_t6, B("ctx"), s), 1);
+        else
+            LAUNCH(CAT_ATTENTION, launch_attention_tc(&qkv_map, &h->pe_map, meta, n_utts, L.max_t6, B("ctx"), s), 1);
         g = GemmArgs();
         g.A = B("ctx"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wo; g.C = B("attn_res"); g.ldc = kHidden;
         g.bias = w.bo; g.R = B("x"); g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kHidden; g.epilogue = EPI_BIAS_RESIDUAL;
@@ -770,6 +787,8 @@ int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
     if (!h || !name) return LOCO_ERR_INVALID;
     if (!strcmp(name, "gemm_impl")) h->gemm_impl = (int)value;
     else if (!strcmp(name, "posconv_impl")) h->posconv_impl = (int)value;
+    else if (!strcmp(name, "attn_impl")) h->attn_impl = (int)value;
+    else if (!strcmp(name, "attn_tc_min_frames")) h->attn_tc_min_frames = (int)value;
     else if (!strcmp(name, "stop_after_layer")) h->stop_after_layer = (int)value;
     else return fail(h, LOCO_ERR_INVALID, std::string("unknown debug knob: ") + name);
     return LOCO_OK;

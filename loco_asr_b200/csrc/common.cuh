@@ -200,6 +200,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -231,6 +244,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
     return d;
 }
+// MN-major operand tile written by TMA with SWIZZLE_128B: 64 MN-elements (128 B) contiguous per K row, 8-row K groups
+// 1024 B apart (SBO); a single 64-wide MN atom, so LBO (stride between MN atoms) is unused.  Pairs with major bit = 1
+// in the instruction descriptor.  (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>, LayoutType::B128.)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (unused: one MN atom)
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO: 8 K-rows x 128 B
+    d |= (uint64_t)1 << 46;                 // version
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
 // Same descriptor family without swizzle (layout type 0), K-major: 8-row x 16-byte core matrices; rows of a core
 // matrix 16 B apart, 8-row groups `sbo` bytes apart, the two 8-element K halves of one MMA `lbo` bytes apart
 // (canonical layout ((8,m),(8,2)):((16B,SBO),(2B,LBO)), cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::K>).
@@ -245,8 +270,9 @@ __device__ __forceinline__ uint64_t umma_desc_noswizzle_kmajor(uint32_t smem_add
 // Instruction descriptor, kind::f16: bf16 A/B (format 1), fp32 accumulate, both operands K-major.
 // Bit layout: `InstrDescriptor` in the same header (c_format [4,6), a_format [7,10), b_format [10,13),
 // n>>3 at [17,23), m>>4 at [24,29)).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int b_mn_major = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -238,6 +238,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 
 int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_rows) {
+    if (g_encode == nullptr) return (int)cudaErrorNotReady;
     cuuint64_t dims[2] = {inner, rows};
     cuuint64_t strides[1] = {row_stride_elems * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
@@ -256,6 +257,11 @@ int launch_t(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, co
 }
 
 }  // namespace
+
+int make_tensor_map_bf16_sw128(void* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
+                               uint32_t box_rows) {
+    return make_map(reinterpret_cast<CUtensorMap*>(map), base, inner, rows, row_stride_elems, box_rows);
+}
 
 int gemm_tc_init() {
     if (g_encode == nullptr) {

@@ -36,6 +36,9 @@ struct GemmArgs {
 // tcgen05/TMEM/TMA GEMM (gemm_tcgen05.cu).  Returns cudaError as int (0 = ok).
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
 int gemm_tc_launch(const GemmArgs& g, int num_sms, cudaStream_t stream);
+// 2-D bf16 tensor map, box = [64 elements (128 B), box_rows], SWIZZLE_128B (gemm_tcgen05.cu owns the driver entry point).
+int make_tensor_map_bf16_sw128(void* map /*CUtensorMap*/, const void* base, uint64_t inner, uint64_t rows,
+                               uint64_t row_stride_elems, uint32_t box_rows);
 // Debug-only SIMT reference GEMM (gemm_simt.cu): used by the tests to cross-check the tensor path.
 int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);
 
@@ -91,6 +94,10 @@ int launch_posconv(const bf16* h, const bf16* w /*[16][128][48 out][48 in]*/, co
 // ---- attention (attention.cu) ------------------------------------------------------------------
 // ctx[r, h*64:(h+1)*64] = softmax_j(q_i.k_j + q_i.pe_k[clip(i-j)+160]) v_j within each utterance.
 int attention_init();
+// tcgen05/TMEM/TMA variant (attention_tc.cu).  maps: qkv [2304, R6] box 128 rows; pe_k [64, 320] box 160 rows.
+int attention_tc_init();
+int launch_attention_tc(const void* qkv_map /*CUtensorMap*/, const void* pe_map /*CUtensorMap*/, const UttMeta* meta, int n_utts,
+                        int max_t6, bf16* ctx /*[R6, 768]*/, cudaStream_t s);
 int launch_attention(const bf16* qkv /*[R6, 2304]*/, const bf16* pe_k /*[320, 64]*/, const UttMeta* meta, int n_utts,
                      int max_t6, bf16* ctx /*[R6, 768]*/, cudaStream_t s);
 

@@ -127,6 +127,8 @@ def run(encoder, items, waves_fn, binarize, folder: str, full_sequence: bool = F
     todo = [it for it in items if not (resume and os.path.exists(output_path(folder, it[0])))]
     if len(todo) < len(items):
         log(f"resume: {len(items) - len(todo)} of {len(items)} outputs already exist")
+    if not todo:
+        return 0
     waves = [waves_fn(it[1]) for it in todo]
     lengths = [len(w) for w in waves]
     targets = binarize([it[2] for it in todo])

@@ -217,3 +217,27 @@ def test_extract_cli_writes_reference_format_and_head_argmax_matches(tmp_path, c
     with open(extract.output_path(extract.output_folder(str(tmp_path), "base", "devel", "audio"), "synth1"), "rb") as fh:
         d = pickle.load(fh)
     assert d["embedding"].shape == (O.frame_lengths(int(slurp_shaped_lengths(3, 1234)[1]))[-1], 768)
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma_sync"])
+def test_attention_kernels_against_oracle(encoder, weights, impl):
+    """Both attention kernels (tcgen05/TMEM product path and the mma.sync cross-check) on a ragged batch whose lengths
+    hit: a single frame, < 1 key block, exactly 128 / 129 frames, > 160 (table clamps), several key blocks."""
+    lengths = [400, 6400, 41200, 41520, 64000, 100000, 250000]     # T = 1, 19, 128, 129, 199, 312, 781
+    waves = H.make_waves(lengths, seed=17)
+    encoder.debug_set("stop_after_layer", 0)
+    encoder.debug_set("attn_impl", impl)
+    try:
+        taps = H.oracle_taps(weights, waves, n_layers=1)
+        pooled, hidden, info = H.run_encoder(encoder, waves)
+        assert info["frames"].tolist() == [1, 19, 128, 129, 199, 312, 781]
+        ctx = encoder.debug_buffer("ctx").float().cpu()
+        for u, t in enumerate(taps):
+            r0 = int(info["rows"][u])
+            ref = t["l0_ctx"]
+            got = ctx[r0:r0 + ref.shape[0]]
+            assert torch.isfinite(got).all(), (impl, u)
+            assert H.rel_err(got, ref) < STAGE_REL_MAX, (impl, u, H.rel_err(got, ref))
+    finally:
+        encoder.debug_set("stop_after_layer", -1)
+        encoder.debug_set("attn_impl", -1)
