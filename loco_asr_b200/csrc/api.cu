@@ -77,7 +77,7 @@ struct loco_handle {
     int gemm_impl = 0;
     int posconv_impl = 0;
     int attn_impl = -1;         // -1 = by length (tcgen05 from attn_tc_min_frames), 0 = tcgen05, 1 = mma.sync
-    int attn_tc_min_frames = 1024;
+    int attn_tc_min_frames = 0;
     alignas(64) CUtensorMap pe_map;   // pe_k [320, 64] for the tcgen05 attention kernel
     int stop_after_layer = -1;
     Layout last;
@@ -637,7 +637,7 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
     // through every later layer -- the tcgen05 attention multiplies masked (P = 0) key rows into O, and 0 * NaN = NaN
     CK(cudaMemsetAsync(ws + L.bufs["ctx"].off, 0, (size_t)L.R6 * kHidden * sizeof(bf16), s));
     alignas(64) CUtensorMap qkv_map;
-    if (make_tensor_map_bf16_sw128(&qkv_map, B("qkv"), 3 * kHidden, (uint64_t)L.R6, 3 * kHidden, 128))
+    if (make_tensor_map_bf16_sw128(&qkv_map, B("qkv"), 3 * kHidden, (uint64_t)L.R6, 3 * kHidden, 32))
         return fail(h, LOCO_ERR_CUDA, "cuTensorMapEncodeTiled failed for qkv");
 
     // ---- conv feature encoder -----------------------------------------------------------------------
@@ -689,7 +689,7 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         if (h->attn_impl == 1 || (h->attn_impl < 0 && L.max_t6 < h->attn_tc_min_frames))
             LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, n_utts, L.max_t6, B("ctx"), s), 1);
         else
-            LAUNCH(CAT_ATTENTION, launch_attention_tc(&qkv_map, &h->pe_map, meta, n_utts, L.max_t6, B("ctx"), s), 1);
+            LAUNCH(CAT_ATTENTION, launch_attention_tc(&qkv_map, &h->pe_map, pc_tiles, (int)L.pc_tiles.size(), B("ctx"), h->num_sms, s), 1);
         g = GemmArgs();
         g.A = B("ctx"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wo; g.C = B("attn_res"); g.ldc = kHidden;
         g.bias = w.bo; g.R = B("x"); g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kHidden; g.epilogue = EPI_BIAS_RESIDUAL;

@@ -4,20 +4,36 @@
 //   S[i, j] = q_i . k_j + q_i . pe_k[clip(i - j, -160, 159) + 160]      (q pre-scaled by 64^-1/2 * log2 e at load)
 //   ctx_i   = sum_j softmax_j(S[i, :]) v_j        over the keys of the SAME utterance only
 //
-// One CTA = 128 queries of one head of one utterance.  TMA brings the Q tile, the whole pe_k table and then
-// 128-key K / V blocks (two-stage ring) into SWIZZLE_128B shared memory; one thread issues every MMA:
-//   G  = Q pe_k^T          128 x 320 (two N = 160 MMAs x 4 K-steps)  -> TMEM, drained once to an fp16 table in smem
-//   S_j = Q K_j^T          128 x 128, double-buffered in TMEM so S_{j+1} is computed while block j's softmax runs
-//   O  += P_j V_j          128 x 64, accumulated IN TMEM; P_j (bf16) goes through a swizzled smem tile as the A operand,
-//                          V_j is consumed as an MN-major B operand exactly as TMA laid it out ([key][dim])
-// Four softmax warps own one query row per thread (TMEM lane == row): tcgen05.ld the 128 scores, add the bias from
-// the thread's own table row (three warp-uniform paths: never clamps / clamps / mixed), online softmax in log2
-// units, rescale O in TMEM only when some row's maximum moved, write P.  The T x T score matrix and the
-// reference's [T, T, 64] position_bias (575 MB at 30 s) never exist.
+// Persistent, warp-specialised: one CTA per SM walks a list of work items (128-query tile x head of one utterance).
+// pe_k (40 KB) is TMA-loaded once per CTA and stays in shared memory; Q tiles (2 slots) and 64-key K / V blocks (8-slot
+// ring) stream in through TMA in 32-row boxes, so a short utterance moves only the rows it has.  One thread issues every
+// MMA (TMEM columns in brackets):
+//   G   = Q pe_k^T         128 x (table columns this tile can reach, <= 320)  [256, 512); columns past 256 in a second round
+//   S_j = Q K_j^T          128 x 64 (N trimmed to the keys that exist)         [0, 64) even j, [64, 128) odd j
+//   O_g += P_j V_j         128 x 64 per block parity g                         [128, 192) / [192, 256)
+//                          A operand P_j is read FROM TMEM (bf16 pairs written by tcgen05.st over the first 32 columns of
+//                          S_j), V_j is the MN-major B operand exactly as TMA laid it out ([key][dim])
+// G is drained once per item into an fp16 table in shared memory (row i of the tile = row of the table), because the
+// bias of key j sits at the per-row offset i - j + 160 -- a skew no TMEM load shape can express.  The reference's
+// [T, T, 64] position_bias (575 MB at 30 s) and the T x T score matrix never exist.
 //
-// mbarrier protocol (all single-CTA): q_full (Q + pe_k landed) -> g_full (G done) -> qt_done (table drained, 128 arrivals);
-// per block j: kv_full[s] / kv_empty[s] (s = j & 1), s_full[b] / s_empty[b] (b = j & 1), p_full (128 arrivals), pv_done.
+// Two softmax groups of four warps ping-pong over the key blocks: group g takes blocks j = g, g+2, ... with one query
+// row per thread (TMEM lane == row), its own score buffer, running maximum, row sum and O accumulator, so the groups
+// never talk inside an item and one runs its exponentials (MUFU) while the other adds bias / takes maxima (LSU, ALU)
+// or waits for its next S.  The running maximum is only raised when some row of the warp would exceed it by more than
+// 2^8 (P stays <= 256), so the O rescale in TMEM is rare.  At the end of an item the two partial results are merged:
+//   O = (2^(m_a - m) O_a + 2^(m_b - m) O_b) / (2^(m_a - m) l_a + 2^(m_b - m) l_b).
+// Per score: LDS.U16 + FHADD (bias), FMNMX3, FADD2, MUFU.EX2, FADD2, F2FP -- about 5 issue slots.
+//
+// Items overlap: G_{n+1} is issued as soon as item n's last S is, S_{n+1,0/1} right after item n's last P.V; the softmax
+// warps drain G_{n+1} into the table and only then run item n's epilogue, hiding the last P.V behind the drain.
+//
+// mbarriers: pe_full; per item q_full[2]/q_empty[2] (slot n & 1), g_full, g_lo_free (first 64 G columns drained, 256
+// arrivals), g2_full (second G round), ga_empty (table complete, 256 arrivals), o_full; per K or V block
+// ring entry kv_full[4]/kv_empty[4]; per key block and group s_full[g], p_full[g] (128 arrivals).  Every softmax thread runs the
+// same barrier skeleton whether or not its rows exist.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -26,285 +42,526 @@ namespace loco {
 
 namespace {
 
-constexpr int FQ = 128;                 // queries per CTA
-constexpr int FK = 128;                 // keys per block
+constexpr int FQ = 128;                 // queries per item
+constexpr int FK = 64;                  // keys per block
+constexpr int NS = 2;                   // ring entries PER GROUP: (V_j | K_{j+2}) pairs, or a lone K for the group's first block of an item
 constexpr int QT_LD = kRelCols + 8;     // fp16 table row pitch (656 B: conflict-free 16-byte row-per-thread stores)
-constexpr int SM_Q = 0;                                   // 128 x 64 bf16
-constexpr int SM_KV = SM_Q + FQ * 128;                    // 2 stages x (K | V), each 128 x 64 bf16; pe_k first lives here
-constexpr int SM_P = SM_KV + 2 * 2 * FK * 128;            // 2 atoms x 128 rows x 128 B
-constexpr int SM_QT = SM_P + 2 * FQ * 128;                // 128 x QT_LD halves
-constexpr int SM_BARS = SM_QT + FQ * QT_LD * 2;
+constexpr int Q_TILE_B = FQ * 128;      // 128 rows x 64 dims bf16
+constexpr int KV_TILE_B = FK * 128;
+constexpr int ENTRY_B = 2 * KV_TILE_B;  // V part, then K part
+constexpr int BOX_ROWS = 32;            // TMA box: 32 rows x 128 B
+constexpr int BOX_B = BOX_ROWS * 128;
+constexpr int SM_PE = 0;
+constexpr int SM_Q = SM_PE + kRelCols * 128;
+constexpr int SM_KV = SM_Q + 2 * Q_TILE_B;
+constexpr int SM_QT = SM_KV + 2 * NS * ENTRY_B;
+constexpr int SM_XM = SM_QT + FQ * QT_LD * 2;        // [2 groups][128 rows] running maxima at the end of an item
+constexpr int SM_XL = SM_XM + 2 * FQ * 4;            // [2 groups][128 rows] row sums
+constexpr int SM_DESC = SM_XL + 2 * FQ * 4;          // 4 x int4 item descriptors: slot n & 3 -- deeper than the Q ring, because a Q slot
+                                                     // is released (S pre-issued) before the softmax warps have read its item's descriptor
+constexpr int SM_BARS = SM_DESC + 64;
 constexpr int FA_SMEM = SM_BARS + 256 + 1024;
-constexpr int FA_THREADS = 192;         // warp 0 loader, warp 1 MMA, warps 2-5 softmax
-constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256, FA_TMEM_COLS = 512;
+static_assert(FA_SMEM <= 232448, "attention_tc: shared memory budget");
+constexpr int FA_SOFTMAX_WARPS = 8;
+constexpr int WARP_LOAD = FA_SOFTMAX_WARPS;                 // warps 8, 9: TMA loaders of group 0 / 1
+constexpr int WARP_MMA = FA_SOFTMAX_WARPS + 2;              // warps 10, 11: MMA issuers of group 0 / 1
+constexpr int FA_THREADS = (FA_SOFTMAX_WARPS + 4) * 32;     // 12 warps: the register file is allocated in 4-warp steps anyway
+constexpr int TM_S = 0, TM_O = 128, TM_G = 256, FA_TMEM_COLS = 512;
+constexpr int G_ROUND1 = 256;           // G columns of the first MMA round
+constexpr float kLazyRescale = 8.0f;    // log2 units
 
 struct __align__(8) FaBars {
-    uint64_t q_full, g_full, qt_done, p_full, pv_done;
-    uint64_t kv_full[2], kv_empty[2], s_full[2], s_empty[2];
+    uint64_t pe_full, g_full, g_lo_free, g2_full, ga_empty, o_full;
+    uint64_t s_full[2], p_full[2];
+    uint64_t q_full[2], q_empty[2], kv_full[2][NS], kv_empty[2][NS];
     uint32_t tmem_base;
 };
+static_assert(sizeof(FaBars) <= 256, "FaBars");
+
+// Key blocks of an utterance: FK keys each, the last one ragged.  Block j covers keys [key0(j), key0(j + 1)).
+// (Equal-sized blocks that give both groups the same work were tried and lost: every block then has a ragged tail and
+// leaves the 32-aligned fast paths of the bias add.)
+__device__ __forceinline__ int num_key_blocks(int T) { return (T + FK - 1) / FK; }
+__device__ __forceinline__ int key0(int j, int T, int n_kv) { return min(j * FK, T); }
+
+struct Item {            // geometry of one (query tile, head) work item
+    int row0;            // row of the tile's first query in the [R6, *] buffers
+    int i0;              // that query's index inside its utterance
+    int T;               // frames of the utterance
+    int head;
+    int nr;              // valid query rows in the tile
+    int n_kv;            // key blocks
+    __device__ __forceinline__ int k0(int j) const { return key0(j, T, n_kv); }
+    __device__ __forceinline__ int klen(int j) const { return key0(j + 1, T, n_kv) - key0(j, T, n_kv); }
+    int cbase;           // first pe_k row (= bias table column) the tile's G covers; multiple of 16
+    int nc16;            // table columns computed (multiple of 16)
+    __device__ __forceinline__ void set(int4 d) {
+        row0 = d.x; i0 = d.y; T = d.z; head = d.w;
+        nr = min(FQ, T - i0);
+        n_kv = num_key_blocks(T);
+        const int c_lo = max(i0 - (T - 1), -kMaxRel) + kMaxRel;
+        const int c_hi = min(i0 + nr - 1, kMaxRel - 1) + kMaxRel;
+        cbase = c_lo & ~15;
+        nc16 = (c_hi - cbase + 16) & ~15;
+    }
+};
+
+__device__ __forceinline__ uint32_t idesc_rt(int n) {      // M = 128, runtime N
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(FQ >> 4) << 24);
+}
+
+// Bounded spin without the printf of common.cuh's mbar_wait (the call would cost this kernel registers and spills).
+// A protocol bug does not hang the GPU: the first wait that runs out records (tag, block, thread, parity) in g_fa_timeout
+// and execution continues with garbage; launch_attention_tc reports it when LOCO_ATTN_DEBUG is set.
+__device__ int g_fa_timeout[4 * 4 + 1];      // [role][tag + 1, block, thread, parity], then a "someone timed out" flag
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
+    uint32_t spins = 0;
+    volatile int* flag = &g_fa_timeout[16];
+    while (!mbar_try_wait(bar, parity))
+        if ((++spins & 1023u) == 0 && (spins > (1u << 20) || (*flag != 0 && spins > (1u << 14)))) {
+            const int role = tag / 100 == 3 ? 2 + (int)(threadIdx.x >> 7) : tag / 100 - 1;
+            *flag = 1;
+            if (atomicCAS(&g_fa_timeout[role * 4], 0, tag + 1) == 0) {
+                g_fa_timeout[role * 4 + 1] = (int)blockIdx.x;
+                g_fa_timeout[role * 4 + 2] = (int)threadIdx.x;
+                g_fa_timeout[role * 4 + 3] = (int)parity;
+            }
+            return;
+        }
+}
 
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__ CUtensorMap pe_map,
-                    const UttMeta* __restrict__ meta, bf16* __restrict__ ctx) {
-    const UttMeta m = meta[blockIdx.z];
-    const int T = m.t6;
-    const int i0 = blockIdx.x * FQ;
-    if (i0 >= T) return;
-    const int head = blockIdx.y;
+                    const PcTile* __restrict__ tiles, int n_items, bf16* __restrict__ ctx) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (sbase - smem_u32(smem_raw));
     FaBars* bars = reinterpret_cast<FaBars*>(smem_al + SM_BARS);
-    __half* sqt = reinterpret_cast<__half*>(smem_al + SM_QT);
+    int4* descs = reinterpret_cast<int4*>(smem_al + SM_DESC);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_kv = (T + FK - 1) / FK;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&qkv_map);
         tma_prefetch_desc(&pe_map);
-        mbar_init(smem_u32(&bars->q_full), 1);
+        mbar_init(smem_u32(&bars->pe_full), 1);
         mbar_init(smem_u32(&bars->g_full), 1);
-        mbar_init(smem_u32(&bars->qt_done), 128);
-        mbar_init(smem_u32(&bars->p_full), 128);
-        mbar_init(smem_u32(&bars->pv_done), 1);
+        mbar_init(smem_u32(&bars->g_lo_free), FA_SOFTMAX_WARPS * 32);
+        mbar_init(smem_u32(&bars->g2_full), 1);
+        mbar_init(smem_u32(&bars->ga_empty), FA_SOFTMAX_WARPS * 32);
+        mbar_init(smem_u32(&bars->o_full), 2);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(smem_u32(&bars->kv_full[s]), 1);
-            mbar_init(smem_u32(&bars->kv_empty[s]), 1);
             mbar_init(smem_u32(&bars->s_full[s]), 1);
-            mbar_init(smem_u32(&bars->s_empty[s]), 128);
+            mbar_init(smem_u32(&bars->p_full[s]), FA_SOFTMAX_WARPS * 16);
+            mbar_init(smem_u32(&bars->q_full[s]), 1);
+            mbar_init(smem_u32(&bars->q_empty[s]), 2);
+        }
+        for (int s = 0; s < 2 * NS; ++s) {
+            mbar_init(smem_u32(&bars->kv_full[0][s]), 1);
+            mbar_init(smem_u32(&bars->kv_empty[0][s]), 1);
         }
         mbar_fence_init();
         fence_proxy_async_smem();
     }
-    if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), FA_TMEM_COLS);
+    if (warp == WARP_MMA) tmem_alloc(smem_u32(&bars->tmem_base), FA_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    const int q_row = m.row6 + i0;          // first row of the Q tile in the [R6, 2304] qkv matrix
-    const int kv_row = m.row6;
 
-    if (warp == 0) {
-        // ===================== loader =====================
+    if (warp == WARP_LOAD || warp == WARP_LOAD + 1) {
+        // ===================== loaders: one per group (group 0's also brings pe_k and the Q tiles) =====================
+        const int g = warp - WARP_LOAD;
         if (lane == 0) {
-            const uint32_t qf = smem_u32(&bars->q_full);
-            mbar_arrive_expect_tx(qf, FQ * 128 + kRelCols * 128);
-            tma_load_2d(sbase + SM_Q, &qkv_map, qf, head * kHeadDim, q_row);
-            tma_load_2d(sbase + SM_KV, &pe_map, qf, 0, 0);
-            tma_load_2d(sbase + SM_KV + 160 * 128, &pe_map, qf, 0, 160);
-            mbar_wait(smem_u32(&bars->qt_done), 0);      // pe_k consumed: its smem becomes the K/V ring
-            for (int j = 0; j < n_kv; ++j) {
-                const int s = j & 1;
-                mbar_wait(smem_u32(&bars->kv_empty[s]), (uint32_t)(((j >> 1) & 1) ^ 1));
-                const uint32_t kf = smem_u32(&bars->kv_full[s]);
-                mbar_arrive_expect_tx(kf, 2 * FK * 128);
-                const uint32_t dst = sbase + SM_KV + s * (2 * FK * 128);
-                tma_load_2d(dst, &qkv_map, kf, kHidden + head * kHeadDim, kv_row + j * FK);
-                tma_load_2d(dst + FK * 128, &qkv_map, kf, 2 * kHidden + head * kHeadDim, kv_row + j * FK);
+            if (g == 0) {
+                const uint32_t pf = smem_u32(&bars->pe_full);
+                mbar_arrive_expect_tx(pf, kRelCols * 128);
+                tma_load_2d(sbase + SM_PE, &pe_map, pf, 0, 0);
+                tma_load_2d(sbase + SM_PE + 160 * 128, &pe_map, pf, 0, 160);
+            }
+            uint32_t e = 0;     // ring entries of this group issued so far
+            int n = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+                const PcTile t = tiles[item / kHeads];
+                const int head = item - (item / kHeads) * kHeads;
+                if (g == 0) {
+                    const int qs = n & 1;
+                    bar_wait(smem_u32(&bars->q_empty[qs]), (uint32_t)(((n >> 1) & 1) ^ 1), 101);
+                    descs[n & 3] = make_int4(t.row0, t.f0, t.t6, head);
+                    const int nr = min(FQ, t.t6 - t.f0);
+                    const int qbox = (nr + BOX_ROWS - 1) / BOX_ROWS;
+                    const uint32_t qf = smem_u32(&bars->q_full[qs]);
+                    mbar_arrive_expect_tx(qf, qbox * BOX_B);
+                    for (int b = 0; b < qbox; ++b)
+                        tma_load_2d(sbase + SM_Q + qs * Q_TILE_B + b * BOX_B, &qkv_map, qf, head * kHeadDim, t.row0 + b * BOX_ROWS);
+                }
+                const int kv_row = t.row0 - t.f0;
+                const int n_kv = num_key_blocks(t.t6);
+                // one ring entry = the operands of one MMA-warp step: V_jv (P.V of block jv) and K_jk (S of block jk = jv + 2);
+                // either may be absent (-1).  Entries are filled in the order the group's MMA warp consumes them.
+                auto load_entry = [&](int jv, int jk) {
+                    const int s = e % NS;
+                    bar_wait(smem_u32(&bars->kv_empty[g][s]), (uint32_t)(((e / NS) & 1) ^ 1), 102);
+                    const uint32_t kf = smem_u32(&bars->kv_full[g][s]);
+                    const int vbox = jv >= 0 ? (key0(jv + 1, t.t6, n_kv) - key0(jv, t.t6, n_kv) + BOX_ROWS - 1) / BOX_ROWS : 0;
+                    const int kbox = jk >= 0 ? (key0(jk + 1, t.t6, n_kv) - key0(jk, t.t6, n_kv) + BOX_ROWS - 1) / BOX_ROWS : 0;
+                    mbar_arrive_expect_tx(kf, (vbox + kbox) * BOX_B);
+                    const uint32_t dst = sbase + SM_KV + (g * NS + s) * ENTRY_B;
+                    for (int b = 0; b < vbox; ++b)
+                        tma_load_2d(dst + b * BOX_B, &qkv_map, kf, 2 * kHidden + head * kHeadDim, kv_row + key0(jv, t.t6, n_kv) + b * BOX_ROWS);
+                    for (int b = 0; b < kbox; ++b)
+                        tma_load_2d(dst + KV_TILE_B + b * BOX_B, &qkv_map, kf, kHidden + head * kHeadDim, kv_row + key0(jk, t.t6, n_kv) + b * BOX_ROWS);
+                    ++e;
+                };
+                if (g < n_kv) load_entry(-1, g);
+                for (int j = g; j < n_kv; j += 2) load_entry(j, j + 2 < n_kv ? j + 2 : -1);
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_g = umma_idesc_bf16(FQ, 160);
-            constexpr uint32_t idesc_s = umma_idesc_bf16(FQ, FK);
-            constexpr uint32_t idesc_o = umma_idesc_bf16(FQ, kHeadDim, /*b MN-major*/ 1);
-            const uint64_t dq = umma_desc_sw128_kmajor(sbase + SM_Q);
-            mbar_wait(smem_u32(&bars->q_full), 0);
-            tc_fence_after();
-            for (int hlf = 0; hlf < 2; ++hlf) {
-                const uint64_t dpe = umma_desc_sw128_kmajor(sbase + SM_KV + hlf * 160 * 128);
+    } else if (warp == WARP_MMA || warp == WARP_MMA + 1) {
+        // ===================== MMA issuers: one per group =====================
+        // Group g's warp issues S_j and P_j.V_j for its blocks j = g, g+2, ...; group 0's also issues G.  The whole warp runs
+        // the (uniform) control flow so descriptors live in uniform registers; one elected lane issues the tcgen05
+        // instructions.  With 32-cycle MMAs (N = 64) the issue path itself is what has to stay short.
+        const int g = warp - WARP_MMA;
+        constexpr uint32_t idesc_o = umma_idesc_bf16(FQ, kHeadDim, /*b MN-major*/ 1);
+        const uint32_t d_s = tmem + TM_S + g * FK, d_o = tmem + TM_O + g * kHeadDim;
+        const uint32_t ring = sbase + SM_KV + g * NS * ENTRY_B;
+        const uint32_t kvf = smem_u32(&bars->kv_full[g][0]), kve = smem_u32(&bars->kv_empty[g][0]);
+        const uint32_t pfull = smem_u32(&bars->p_full[g]), sfull = smem_u32(&bars->s_full[g]);
+        uint32_t e = 0;                     // ring entries consumed so far
+        uint32_t cnt = 0;                   // key blocks handled (parity of p_full)
+        auto issue_g = [&](const Item& it, int qs, int round) {
+            const uint64_t dq = umma_desc_sw128_kmajor(sbase + SM_Q + qs * Q_TILE_B);
+            const uint64_t dp = umma_desc_sw128_kmajor(sbase + SM_PE + (it.cbase + round * G_ROUND1) * 128);
+            const uint32_t id = idesc_rt(round ? it.nc16 - G_ROUND1 : min(it.nc16, G_ROUND1));
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tmem + hlf * 160, dq + (uint64_t)(k * 2), dpe + (uint64_t)(k * 2), idesc_g, k);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem + TM_G, dq + (uint64_t)(k * 2), dp + (uint64_t)(k * 2), id, k);
+                umma_commit(smem_u32(round ? &bars->g2_full : &bars->g_full));
             }
-            umma_commit(smem_u32(&bars->g_full));
-            mbar_wait(smem_u32(&bars->qt_done), 0);      // G drained: its TMEM columns become S0 / S1 / O
-            tc_fence_after();
-            auto issue_s = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(smem_u32(&bars->kv_full[s]), (uint32_t)((j >> 1) & 1));
-                mbar_wait(smem_u32(&bars->s_empty[s]), (uint32_t)(((j >> 1) & 1) ^ 1));
-                tc_fence_after();
-                const uint64_t dk = umma_desc_sw128_kmajor(sbase + SM_KV + s * (2 * FK * 128));
+        };
+        // S_j = Q K_j^T from the K part of ring entry `slot`
+        auto issue_s = [&](const Item& it, int qs, int j, int slot) {
+            const uint64_t dq = umma_desc_sw128_kmajor(sbase + SM_Q + qs * Q_TILE_B);
+            const uint64_t dk = umma_desc_sw128_kmajor(ring + slot * ENTRY_B + KV_TILE_B);
+            const uint32_t id = idesc_rt((it.klen(j) + 15) & ~15);
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tmem + (s ? TM_S1 : TM_S0), dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k);
-                umma_commit(smem_u32(&bars->s_full[s]));
-            };
-            issue_s(0);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) issue_s(j + 1);
-                mbar_wait(smem_u32(&bars->p_full), (uint32_t)(j & 1));
+                for (int k = 0; k < 4; ++k) umma_bf16(d_s, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), id, k);
+                umma_commit(sfull);
+            }
+        };
+        // the group's first block of an item, from a lone-K entry; releases Q if that was the group's only S
+        auto issue_s_first = [&](const Item& it, int qs) {
+            if (g < it.n_kv) {
+                const int slot = e % NS;
+                bar_wait(kvf + slot * 8, (e / NS) & 1, 203);
                 tc_fence_after();
-                const uint32_t v_base = sbase + SM_KV + (j & 1) * (2 * FK * 128) + FK * 128;
-#pragma unroll
-                for (int k = 0; k < FK / 16; ++k) {
-                    const uint64_t dp = umma_desc_sw128_kmajor(sbase + SM_P + (k >> 2) * (FQ * 128) + (k & 3) * 32);
-                    const uint64_t dv = umma_desc_sw128_mnmajor(v_base + k * (16 * 128));
-                    umma_bf16(tmem + TM_O, dp, dv, idesc_o, (j | k) != 0 ? 1u : 0u);
+                issue_s(it, qs, g, slot);
+                if (elect_one()) umma_commit(kve + slot * 8);
+                ++e;
+            }
+        };
+        // this warp's part of "Q slot free": after its last S (and, for group 0, after the last G round)
+        auto release_q = [&](const Item& it, int qs) {
+            if (elect_one()) {
+                if (g < it.n_kv || g == 0) umma_commit(smem_u32(&bars->q_empty[qs]));
+                else mbar_arrive(smem_u32(&bars->q_empty[qs]));
+            }
+        };
+        Item cur, nxt;
+        if (g == 0) bar_wait(smem_u32(&bars->pe_full), 0, 204);
+        bar_wait(smem_u32(&bars->q_full[0]), 0, 205);
+        cur.set(descs[0]);
+        tc_fence_after();
+        if (g == 0) issue_g(cur, 0, 0);
+        issue_s_first(cur, 0);
+        int n = 0;
+        for (int item = blockIdx.x;; item += gridDim.x, ++n) {
+            const int qs = n & 1;
+            const bool has_next = item + (int)gridDim.x < n_items;
+            if (g == 0 && cur.nc16 > G_ROUND1) {       // second G round over the first 64 columns, once they are drained
+                bar_wait(smem_u32(&bars->g_lo_free), (uint32_t)(n & 1), 206);
+                tc_fence_after();
+                issue_g(cur, qs, 1);
+            }
+            bool ga_seen = false;
+            // after this warp's last S of the item: release Q, look at the next item, (group 0) issue its G
+            auto after_last_s = [&]() {
+                release_q(cur, qs);
+                if (!has_next) return;
+                if (g == 0) {
+                    bar_wait(smem_u32(&bars->ga_empty), (uint32_t)(n & 1), 207);      // this item's table has left TMEM
+                    ga_seen = true;
                 }
-                umma_commit(smem_u32(&bars->pv_done));
-                umma_commit(smem_u32(&bars->kv_empty[j & 1]));
+                bar_wait(smem_u32(&bars->q_full[qs ^ 1]), (uint32_t)(((n + 1) >> 1) & 1), 205);
+                nxt.set(descs[(n + 1) & 3]);
+                tc_fence_after();
+                if (g == 0) issue_g(nxt, qs ^ 1, 0);
+            };
+            if (g + 2 >= cur.n_kv) after_last_s();      // the pre-issued S was this warp's only one
+            for (int j = g; j < cur.n_kv; j += 2, ++e, ++cnt) {
+                const int slot = e % NS;
+                bar_wait(pfull, cnt & 1, 208);
+                bar_wait(kvf + slot * 8, (e / NS) & 1, 203);
+                tc_fence_after();
+                const uint64_t dv = umma_desc_sw128_mnmajor(ring + slot * ENTRY_B);
+                const int valid = cur.klen(j);
+                const uint32_t acc0 = j >= 2 ? 1u : 0u;
+                if (valid >= FK) {           // full block: four K = 16 steps, 16 V rows (2048 B) each
+                    if (elect_one()) {
+                        umma_bf16_ts(d_o, d_s, dv, idesc_o, acc0);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k) umma_bf16_ts(d_o, d_s + k * 8, dv + (uint64_t)(k * 128), idesc_o, 1u);
+                    }
+                } else {
+                    const int ks = (valid + 15) >> 4;
+                    if (elect_one())
+                        for (int k = 0; k < ks; ++k) umma_bf16_ts(d_o, d_s + k * 8, dv + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : acc0);
+                }
+                if (j + 2 < cur.n_kv) issue_s(cur, qs, j + 2, slot);
+                if (elect_one()) umma_commit(kve + slot * 8);
+                if (j + 2 < cur.n_kv && j + 4 >= cur.n_kv) after_last_s();
             }
+            // o_full needs both groups' last P.V; it may only complete once every softmax thread has seen the previous
+            // item's o_full (ga_empty), so a waiter is never lapped by two phases
+            if (!ga_seen) bar_wait(smem_u32(&bars->ga_empty), (uint32_t)(n & 1), 207);
+            if (elect_one()) {
+                if (g < cur.n_kv) umma_commit(smem_u32(&bars->o_full));
+                else mbar_arrive(smem_u32(&bars->o_full));
+            }
+            if (!has_next) break;
+            issue_s_first(nxt, qs ^ 1);
+            cur = nxt;
         }
     } else {
-        // ===================== softmax warps: one query row per thread =====================
+        // ===================== softmax warps =====================
         const int q = warp & 3;                    // TMEM lane quadrant
+        const int g = warp >> 2;                   // group: key blocks j = g, g + 2, ...
         const int row = q * 32 + lane;
-        const int i = i0 + row;                    // query index inside the utterance (rows >= T are never stored)
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-        __half* my_qt = sqt + row * QT_LD;
+        const uint32_t t_s = t_lane + TM_S + g * FK;
+        const uint32_t t_o = t_lane + TM_O + g * kHeadDim;
+        __half* my_qt = reinterpret_cast<__half*>(smem_al + SM_QT) + row * QT_LD;
+        float* xm = reinterpret_cast<float*>(smem_al + SM_XM);
+        float* xl = reinterpret_cast<float*>(smem_al + SM_XL);
+        const int bar_id = 1 + q;
 
-        // ---- drain G (Q pe_k^T) into this row of the fp16 bias table ------------------------------------------
-        mbar_wait(smem_u32(&bars->g_full), 0);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < kRelCols / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_lane + c * 32, v);
-            tmem_ld_wait(v);
-#pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-                uint4 o4;
-                __half2 h;
-                h = __floats2half2_rn(__uint_as_float(v[e + 0]), __uint_as_float(v[e + 1])); o4.x = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])); o4.y = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5])); o4.z = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7])); o4.w = *reinterpret_cast<uint32_t*>(&h);
-                *reinterpret_cast<uint4*>(my_qt + c * 32 + e) = o4;
-            }
-        }
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bars->qt_done));
+        // deferred epilogue state (previous item)
+        bool prev_active = false, prev_store = false, prev_two = false;
+        bf16* prev_out = nullptr;
+        uint32_t cnt = 0;                          // key blocks this group has seen (parity of s_full[g])
+        uint32_t n_g2 = 0;                         // items that needed a second G round
 
-        float row_max = -INFINITY, row_sum = 0.f;
-        const int iw0 = i0 + q * 32;               // first query row of this warp
-        const int ic = min(i, T - 1);              // clamped row for table indexing on the slow path
-        for (int j = 0; j < n_kv; ++j) {
-            const int b = j & 1;
-            const int j0 = j * FK;
-            mbar_wait(smem_u32(&bars->s_full[b]), (uint32_t)((j >> 1) & 1));
+        int n = 0;
+        auto epilogue = [&]() {                    // item n - 1
+            bar_wait(smem_u32(&bars->o_full), (uint32_t)((n - 1) & 1), 309);
             tc_fence_after();
-            uint32_t su[FK / 32][32];
+            if (prev_active) {
+                const float ma = xm[row], mb = xm[FQ + row];
+                const float m = fmaxf(ma, mb);
+                float wa = ex2_approx(ma - m), wb = ex2_approx(mb - m);
+                const float inv = 1.0f / (wa * xl[row] + wb * xl[FQ + row]);
+                wa *= inv;
+                wb *= inv;
 #pragma unroll
-            for (int c = 0; c < FK / 32; ++c) tmem_ld_32x32(t_lane + (b ? TM_S1 : TM_S0) + c * 32, su[c]);
-            tmem_ld_wait();
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t va[16], vb[16];
+                    tmem_ld_32x16(t_lane + TM_O + g * 32 + hh * 16, va);
+                    if (prev_two) tmem_ld_32x16(t_lane + TM_O + kHeadDim + g * 32 + hh * 16, vb);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < FK / 32; ++c)
+                    for (int e = 0; e < 16; ++e) {
+                        asm volatile("" : "+r"(va[e]));
+                        asm volatile("" : "+r"(vb[e]));
+                    }
+                    float o[16];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) asm volatile("" : "+r"(su[c][e]));
-            float sc[FK];
+                    for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(va[e]) * wa;
+                    if (prev_two) {
 #pragma unroll
-            for (int c = 0; c < FK / 32; ++c)
+                        for (int e = 0; e < 16; ++e) o[e] = fmaf(__uint_as_float(vb[e]), wb, o[e]);
+                    }
+                    if (prev_store) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) sc[c * 32 + e] = __uint_as_float(su[c][e]);
-            tc_fence_before();
-            mbar_arrive(smem_u32(&bars->s_empty[b]));      // S buffer may be overwritten by S_{j+2}
+                        for (int e = 0; e < 16; e += 8) {
+                            uint4 o4;
+                            o4.x = pack_bf16(o[e + 0], o[e + 1]);
+                            o4.y = pack_bf16(o[e + 2], o[e + 3]);
+                            o4.z = pack_bf16(o[e + 4], o[e + 5]);
+                            o4.w = pack_bf16(o[e + 6], o[e + 7]);
+                            *reinterpret_cast<uint4*>(prev_out + hh * 16 + e) = o4;
+                        }
+                    }
+                }
+                tc_fence_before();
+                named_bar_sync(bar_id, 64);       // both groups have read both accumulators before either P.V restarts them
+            }
+        };
 
-            // ---- + relative-position bias, key mask, row maximum ----------------------------------------------
-            float mx = row_max;
-            float cbias[FK / 32];                  // per-chunk scalar bias (clamped regions), folded into the exp argument
-#pragma unroll
-            for (int c = 0; c < FK / 32; ++c) {
-                const int jc = j0 + c * 32;
-                const int rel_max = iw0 + 31 - jc, rel_min = iw0 - (jc + 31);
-                cbias[c] = 0.f;
-                if (jc >= T) continue;             // whole chunk past the utterance: skipped again below
-                if (rel_max < kMaxRel && rel_min >= -kMaxRel) {
-                    const __half* base = my_qt + (i - jc + kMaxRel);      // column for key jc; key jc+e is e columns lower
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) sc[c * 32 + e] += __half2float(base[-e]);
-                } else if (rel_min >= kMaxRel - 1 || rel_max <= -kMaxRel) {
-                    cbias[c] = __half2float(my_qt[rel_min >= kMaxRel - 1 ? kRelCols - 1 : 0]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int rel = max(-kMaxRel, min(kMaxRel - 1, ic - (jc + e))) + kMaxRel;
-                        sc[c * 32 + e] += __half2float(my_qt[rel]);
-                    }
-                }
-                if (jc + 32 > T) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (jc + e >= T) sc[c * 32 + e] = -INFINITY;
-                }
-                float cm = sc[c * 32];
-#pragma unroll
-                for (int e = 1; e < 32; ++e) cm = fmaxf(cm, sc[c * 32 + e]);
-                mx = fmaxf(mx, cm + cbias[c]);
-            }
-            const float corr = ex2_approx(row_max - mx);      // first block: exp2(-inf) = 0
-            row_max = mx;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+            // G_n complete also means the item's descriptor is in place (the MMA warp read it before issuing G_n).  The
+            // Q barriers cannot be used for that: a Q slot may be released and refilled before a softmax thread looks.
+            bar_wait(smem_u32(&bars->g_full), (uint32_t)(n & 1), 310);
+            tc_fence_after();
+            Item it;
+            it.set(descs[n & 3]);
+            const bool active = q * 32 < it.nr;    // same for both warps of a row quad
+            const int i = it.i0 + row;             // query index inside the utterance (rows >= T are never stored)
 
-            // ---- O (in TMEM) and the P tile are free once PV_{j-1} has completed ----------------------------
-            if (j > 0) {
-                mbar_wait(smem_u32(&bars->pv_done), (uint32_t)((j - 1) & 1));
-                tc_fence_after();
-                if (!__all_sync(0xffffffffu, corr == 1.0f)) {     // some row's maximum moved: rescale this warp's O rows
-#pragma unroll
-                    for (int c = 0; c < kHeadDim / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_lane + TM_O + c * 32, v);
-                        tmem_ld_wait(v);
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * corr);
-                        tmem_st_32x32(t_lane + TM_O + c * 32, v);
-                    }
-                    tmem_st_wait();
-                }
-            }
-            // ---- P = exp2(S - max) as bf16 into the swizzled A-operand tile -----------------------------------
-            float ps = 0.f;
-            const uint32_t p_row = sbase + SM_P + row * 128;
-#pragma unroll
-            for (int kk = 0; kk < FK / 8; ++kk) {          // 16-byte chunks of 8 keys
-                uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
-                if (j0 + (kk >> 2) * 32 < T) {             // chunks wholly past the utterance: P = 0, no exps
-                    const float sub = mx - cbias[kk >> 2];
-                    float p[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        p[e] = ex2_approx(sc[kk * 8 + e] - sub);
-                        ps += p[e];
-                    }
-                    o4.x = pack_bf16(p[0], p[1]);
-                    o4.y = pack_bf16(p[2], p[3]);
-                    o4.z = pack_bf16(p[4], p[5]);
-                    o4.w = pack_bf16(p[6], p[7]);
-                }
-                sts128(p_row + (kk >> 3) * (FQ * 128) + (((kk & 7) ^ (row & 7)) << 4), o4);
-            }
-            row_sum = row_sum * corr + ps;
-            fence_proxy_async_smem();     // P (generic proxy) -> visible to the tensor core's async proxy
-            tc_fence_before();
-            mbar_arrive(smem_u32(&bars->p_full));
-        }
-        // ---- epilogue: O / l -> bf16 -> ctx -------------------------------------------------------------------
-        mbar_wait(smem_u32(&bars->pv_done), (uint32_t)((n_kv - 1) & 1));
-        tc_fence_after();
-        const float inv = 1.0f / row_sum;
-        bf16* orow = ctx + (int64_t)(m.row6 + i) * kHidden + head * kHeadDim;
-#pragma unroll
-        for (int c = 0; c < kHeadDim / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_lane + TM_O + c * 32, v);
-            tmem_ld_wait(v);
-            if (i < T) {
+            // ---- drain G (Q pe_k^T) into this row of the fp16 bias table; the two groups split the 32-column chunks -----
+            if (active || prev_active) named_bar_sync(bar_id, 64);   // the other group is done with the previous item's table rows
+                                                                      // and has published its maxima / sums
+            const int n_chunks = (it.nc16 + 31) >> 5;
+            auto drain = [&](int c, int tcol) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_lane + TM_G + tcol, v);
+                tmem_ld_wait(v);
+                __half* dst = my_qt + c * 32;
 #pragma unroll
                 for (int e = 0; e < 32; e += 8) {
                     uint4 o4;
-                    o4.x = pack_bf16(__uint_as_float(v[e + 0]) * inv, __uint_as_float(v[e + 1]) * inv);
-                    o4.y = pack_bf16(__uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv);
-                    o4.z = pack_bf16(__uint_as_float(v[e + 4]) * inv, __uint_as_float(v[e + 5]) * inv);
-                    o4.w = pack_bf16(__uint_as_float(v[e + 6]) * inv, __uint_as_float(v[e + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + e) = o4;
+                    __half2 h;
+                    h = __floats2half2_rn(__uint_as_float(v[e + 0]), __uint_as_float(v[e + 1])); o4.x = *reinterpret_cast<uint32_t*>(&h);
+                    h = __floats2half2_rn(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])); o4.y = *reinterpret_cast<uint32_t*>(&h);
+                    h = __floats2half2_rn(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5])); o4.z = *reinterpret_cast<uint32_t*>(&h);
+                    h = __floats2half2_rn(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7])); o4.w = *reinterpret_cast<uint32_t*>(&h);
+                    *reinterpret_cast<uint4*>(dst + e) = o4;
                 }
+            };
+            if (active && g < n_chunks) drain(g, g * 32);                  // chunks 0 / 1 first: round two reuses their columns
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars->g_lo_free));
+            if (active)
+                for (int c = g + 2; c < min(n_chunks, 8); c += 2) drain(c, c * 32);
+            if (it.nc16 > G_ROUND1) {
+                bar_wait(smem_u32(&bars->g2_full), n_g2 & 1, 311);
+                ++n_g2;
+                tc_fence_after();
+                if (active && 8 + g < n_chunks) drain(8 + g, g * 32);
             }
+            if (active) named_bar_sync(bar_id, 64);       // both column sets of my rows are in place
+
+            // ---- previous item's epilogue (its last P.V ran while the table was drained) ---------------------------------
+            if (n > 0) epilogue();
+            // G has left TMEM -- and this thread has seen o_full of the previous item, so o_full (which the MMA warp only
+            // completes for item n after this barrier) can never run two phases ahead of a waiter
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars->ga_empty));
+
+            float row_max = -INFINITY, row_sum = 0.f;
+            const int iw0 = it.i0 + q * 32;            // first query row of this warp
+            const int ic = min(i, it.T - 1);           // clamped row for table indexing on the slow path
+            const int col0 = i + kMaxRel - it.cbase;   // table column of key 0
+            for (int j = g; j < it.n_kv; j += 2, ++cnt) {
+                const int j0 = it.k0(j), jlen = it.klen(j);
+                const int nch = active ? (jlen + 31) >> 5 : 0;      // 32-key chunks that hold keys
+                bar_wait(smem_u32(&bars->s_full[g]), cnt & 1, 312);      // also: this group's previous P.V has completed
+                tc_fence_after();
+                uint32_t su[2][32];                // scores, fp32 bit patterns (one array from the TMEM load to the exponentials)
+                if (nch > 0) tmem_ld_32x32(t_s, su[0]);
+                if (nch > 1) tmem_ld_32x32(t_s + 32, su[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) asm volatile("" : "+r"(su[c][e]));
+#define SC(c, e) __uint_as_float(su[c][e])
+#define SET_SC(c, e, v) su[c][e] = __float_as_uint(v)
+                float cbias[2] = {0.f, 0.f};       // per-chunk scalar bias (clamped regions), folded into the exp argument
+                float mloc = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c >= nch) continue;
+                    const int jc = j0 + c * 32;
+                    const int rel_max = iw0 + 31 - jc, rel_min = iw0 - (jc + 31);
+                    if (rel_max < kMaxRel && rel_min >= -kMaxRel) {
+                        const unsigned short* base = reinterpret_cast<const unsigned short*>(my_qt) + (col0 - jc);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) SET_SC(c, e, add_f32_f16(SC(c, e), base[-e]));
+                    } else if (rel_min >= kMaxRel - 1 || rel_max <= -kMaxRel) {
+                        cbias[c] = __half2float(my_qt[(rel_min >= kMaxRel - 1 ? kRelCols - 1 : 0) - it.cbase]);
+                    } else {
+                        const unsigned short* base = reinterpret_cast<const unsigned short*>(my_qt) + (kMaxRel - it.cbase);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const int rel = max(-kMaxRel, min(kMaxRel - 1, ic - (jc + e)));
+                            SET_SC(c, e, add_f32_f16(SC(c, e), base[rel]));
+                        }
+                    }
+                    if (c * 32 + 32 > jlen) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (c * 32 + e >= jlen) SET_SC(c, e, -INFINITY);
+                    }
+                    float cm[4] = {SC(c, 0), SC(c, 1), SC(c, 2), SC(c, 3)};      // four chains for ILP
+#pragma unroll
+                    for (int e = 4; e < 32; e += 4) {
+                        cm[0] = fmaxf(cm[0], SC(c, e + 0));
+                        cm[1] = fmaxf(cm[1], SC(c, e + 1));
+                        cm[2] = fmaxf(cm[2], SC(c, e + 2));
+                        cm[3] = fmaxf(cm[3], SC(c, e + 3));
+                    }
+                    mloc = fmaxf(mloc, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) + cbias[c]);
+                }
+                if (active && __any_sync(0xffffffffu, mloc > row_max + kLazyRescale)) {
+                    const float mx = fmaxf(row_max, mloc);
+                    const float corr = ex2_approx(row_max - mx);      // first block: exp2(-inf) = 0
+                    row_max = mx;
+                    row_sum *= corr;
+                    if (j >= 2) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(t_o + hh * 32, v);
+                            tmem_ld_wait(v);
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * corr);
+                            tmem_st_32x32(t_o + hh * 32, v);
+                        }
+                    }
+                }
+                // ---- P = exp2(S - max) as packed bf16 pairs over the first 32 columns of this group's S buffer -------------
+                float2 ps[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c >= nch) continue;
+                    const float sub = cbias[c] - row_max;
+                    const float2 sub2 = make_float2(sub, sub);
+                    uint32_t pp[16];
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        const float2 d = add_f32x2(make_float2(SC(c, e), SC(c, e + 1)), sub2);
+                        const float2 p = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+                        ps[(e >> 1) & 1] = add_f32x2(ps[(e >> 1) & 1], p);
+                        pp[e >> 1] = pack_bf16(p.x, p.y);
+                    }
+                    tmem_st_32x16(t_s + c * 16, pp);
+                }
+                row_sum += (ps[0].x + ps[0].y) + (ps[1].x + ps[1].y);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars->p_full[g]));
+#undef SC
+#undef SET_SC
+            }
+            // ---- partial results of this group; the epilogue is deferred behind the next item's table drain ---------------
+            prev_active = active;
+            if (active) {
+                xm[g * FQ + row] = row_max;
+                xl[g * FQ + row] = row_sum;
+                prev_store = i < it.T;
+                prev_two = it.n_kv > 1;
+                prev_out = ctx + (int64_t)(it.row0 + row) * kHidden + it.head * kHeadDim + g * 32;
+            }
+        }
+        if (n > 0) {
+            if (prev_active) named_bar_sync(bar_id, 64);      // the other group's maxima / sums are in place
+            epilogue();
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == WARP_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem, FA_TMEM_COLS);
     }
@@ -316,13 +573,29 @@ int attention_tc_init() {
     return (int)cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
 }
 
-int launch_attention_tc(const void* qkv_map, const void* pe_map, const UttMeta* meta, int n_utts, int max_t6, bf16* ctx,
+int launch_attention_tc(const void* qkv_map, const void* pe_map, const PcTile* tiles, int n_tiles, bf16* ctx, int num_sms,
                         cudaStream_t s) {
-    if (n_utts <= 0 || max_t6 <= 0) return 0;
-    dim3 grid((max_t6 + FQ - 1) / FQ, kHeads, n_utts);
+    if (n_tiles <= 0) return 0;
+    const int n_items = n_tiles * kHeads;
+    const int grid = n_items < num_sms ? n_items : num_sms;
     attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(*reinterpret_cast<const CUtensorMap*>(qkv_map),
-                                                          *reinterpret_cast<const CUtensorMap*>(pe_map), meta, ctx);
-    return (int)cudaGetLastError();
+                                                          *reinterpret_cast<const CUtensorMap*>(pe_map), tiles, n_items, ctx);
+    int rc = (int)cudaGetLastError();
+    static const bool debug = getenv("LOCO_ATTN_DEBUG") != nullptr;
+    if (debug && !rc) {
+        int t[17] = {0};
+        rc = (int)cudaStreamSynchronize(s);
+        if (!rc) rc = (int)cudaMemcpyFromSymbol(t, g_fa_timeout, sizeof t);
+        if (t[16]) {
+            for (int r = 0; r < 4; ++r)
+                if (t[r * 4])
+                    fprintf(stderr, "loco: attention_tc wait timed out: role %d tag %d block %d thread %d parity %d (items %d grid %d)\n", r,
+                            t[r * 4] - 1, t[r * 4 + 1], t[r * 4 + 2], t[r * 4 + 3], n_items, grid);
+            int z[17] = {0};
+            cudaMemcpyToSymbol(g_fa_timeout, z, sizeof z);
+        }
+    }
+    return rc;
 }
 
 }  // namespace loco

@@ -94,10 +94,11 @@ int launch_posconv(const bf16* h, const bf16* w /*[16][128][48 out][48 in]*/, co
 // ---- attention (attention.cu) ------------------------------------------------------------------
 // ctx[r, h*64:(h+1)*64] = softmax_j(q_i.k_j + q_i.pe_k[clip(i-j)+160]) v_j within each utterance.
 int attention_init();
-// tcgen05/TMEM/TMA variant (attention_tc.cu).  maps: qkv [2304, R6] box 128 rows; pe_k [64, 320] box 160 rows.
+// tcgen05/TMEM/TMA kernel (attention_tc.cu), persistent over (128-query tile, head) items.  maps: qkv [2304, R6] box 32 rows;
+// pe_k [64, 320] box 160 rows.  `tiles` is the positional conv's tile list (same 128-frame tiling of every utterance).
 int attention_tc_init();
-int launch_attention_tc(const void* qkv_map /*CUtensorMap*/, const void* pe_map /*CUtensorMap*/, const UttMeta* meta, int n_utts,
-                        int max_t6, bf16* ctx /*[R6, 768]*/, cudaStream_t s);
+int launch_attention_tc(const void* qkv_map /*CUtensorMap*/, const void* pe_map /*CUtensorMap*/, const PcTile* tiles, int n_tiles,
+                        bf16* ctx /*[R6, 768]*/, int num_sms, cudaStream_t s);
 int launch_attention(const bf16* qkv /*[R6, 2304]*/, const bf16* pe_k /*[320, 64]*/, const UttMeta* meta, int n_utts,
                      int max_t6, bf16* ctx /*[R6, 768]*/, cudaStream_t s);
 
