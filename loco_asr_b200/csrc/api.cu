@@ -77,7 +77,7 @@ struct loco_handle {
     int gemm_impl = 0;
     int posconv_impl = 0;
     int attn_impl = -1;         // -1 = by length (tcgen05 from attn_tc_min_frames), 0 = tcgen05, 1 = mma.sync
-    int attn_tc_min_frames = 0;
+    int attn_tc_min_frames = 176;
     alignas(64) CUtensorMap pe_map;   // pe_k [320, 64] for the tcgen05 attention kernel
     int stop_after_layer = -1;
     Layout last;

@@ -66,13 +66,14 @@ constexpr int FA_SOFTMAX_WARPS = 8;
 constexpr int WARP_LOAD = FA_SOFTMAX_WARPS;                 // warps 8, 9: TMA loaders of group 0 / 1
 constexpr int WARP_MMA = FA_SOFTMAX_WARPS + 2;              // warps 10, 11: MMA issuers of group 0 / 1
 constexpr int FA_THREADS = (FA_SOFTMAX_WARPS + 4) * 32;     // 12 warps: the register file is allocated in 4-warp steps anyway
-constexpr int TM_S = 0, TM_O = 128, TM_G = 256, FA_TMEM_COLS = 512;
-constexpr int G_ROUND1 = 256;           // G columns of the first MMA round
+constexpr int TM_S = 0, TM_P = 128, TM_O = 192, TM_G = 320, FA_TMEM_COLS = 512;   // S 2x64, P 2x32, O 2x64, G 192
+constexpr int G_ROUND1 = 192;           // G columns of the first MMA round (6 chunks); the rest reuses the first 128 columns
+constexpr int G_LO_CHUNKS = 4;          // chunks that must be drained before the second round may be issued
 constexpr float kLazyRescale = 8.0f;    // log2 units
 
 struct __align__(8) FaBars {
     uint64_t pe_full, g_full, g_lo_free, g2_full, ga_empty, o_full;
-    uint64_t s_full[2], p_full[2];
+    uint64_t s_full[2], s_empty[2], p_full[2], pv_done[2];
     uint64_t q_full[2], q_empty[2], kv_full[2][NS], kv_empty[2][NS];
     uint32_t tmem_base;
 };
@@ -152,6 +153,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&bars->s_full[s]), 1);
             mbar_init(smem_u32(&bars->p_full[s]), FA_SOFTMAX_WARPS * 16);
+            mbar_init(smem_u32(&bars->s_empty[s]), FA_SOFTMAX_WARPS * 16);
+            mbar_init(smem_u32(&bars->pv_done[s]), 1);
             mbar_init(smem_u32(&bars->q_full[s]), 1);
             mbar_init(smem_u32(&bars->q_empty[s]), 2);
         }
@@ -223,12 +226,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         // instructions.  With 32-cycle MMAs (N = 64) the issue path itself is what has to stay short.
         const int g = warp - WARP_MMA;
         constexpr uint32_t idesc_o = umma_idesc_bf16(FQ, kHeadDim, /*b MN-major*/ 1);
-        const uint32_t d_s = tmem + TM_S + g * FK, d_o = tmem + TM_O + g * kHeadDim;
+        const uint32_t d_s = tmem + TM_S + g * FK, d_p = tmem + TM_P + g * (FK / 2), d_o = tmem + TM_O + g * kHeadDim;
         const uint32_t ring = sbase + SM_KV + g * NS * ENTRY_B;
         const uint32_t kvf = smem_u32(&bars->kv_full[g][0]), kve = smem_u32(&bars->kv_empty[g][0]);
         const uint32_t pfull = smem_u32(&bars->p_full[g]), sfull = smem_u32(&bars->s_full[g]);
+        const uint32_t sempty = smem_u32(&bars->s_empty[g]), pvdone = smem_u32(&bars->pv_done[g]);
         uint32_t e = 0;                     // ring entries consumed so far
-        uint32_t cnt = 0;                   // key blocks handled (parity of p_full)
+        uint32_t n_s = 0;                   // S blocks issued by this warp (block k may be issued once block k-1 was read: s_empty)
+        uint32_t n_pv = 0;                  // P.V products issued (parity of p_full)
         auto issue_g = [&](const Item& it, int qs, int round) {
             const uint64_t dq = umma_desc_sw128_kmajor(sbase + SM_Q + qs * Q_TILE_B);
             const uint64_t dp = umma_desc_sw128_kmajor(sbase + SM_PE + (it.cbase + round * G_ROUND1) * 128);
@@ -239,8 +244,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 umma_commit(smem_u32(round ? &bars->g2_full : &bars->g_full));
             }
         };
-        // S_j = Q K_j^T from the K part of ring entry `slot`
+        // S_j = Q K_j^T from the K part of ring entry `slot`, as soon as the group has read its previous S out of TMEM
         auto issue_s = [&](const Item& it, int qs, int j, int slot) {
+            if (n_s > 0) bar_wait(sempty, (n_s - 1) & 1, 213);
+            ++n_s;
+            tc_fence_after();
             const uint64_t dq = umma_desc_sw128_kmajor(sbase + SM_Q + qs * Q_TILE_B);
             const uint64_t dk = umma_desc_sw128_kmajor(ring + slot * ENTRY_B + KV_TILE_B);
             const uint32_t id = idesc_rt((it.klen(j) + 15) & ~15);
@@ -250,16 +258,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 umma_commit(sfull);
             }
         };
-        // the group's first block of an item, from a lone-K entry; releases Q if that was the group's only S
-        auto issue_s_first = [&](const Item& it, int qs) {
-            if (g < it.n_kv) {
-                const int slot = e % NS;
-                bar_wait(kvf + slot * 8, (e / NS) & 1, 203);
-                tc_fence_after();
-                issue_s(it, qs, g, slot);
-                if (elect_one()) umma_commit(kve + slot * 8);
-                ++e;
-            }
+        // the group's first block of an item, from the lone-K ring entry `ee`
+        auto issue_s_first = [&](const Item& it, int qs, uint32_t ee) {
+            const int slot = ee % NS;
+            bar_wait(kvf + slot * 8, (ee / NS) & 1, 203);
+            issue_s(it, qs, g, slot);
+            if (elect_one()) umma_commit(kve + slot * 8);
         };
         // this warp's part of "Q slot free": after its last S (and, for group 0, after the last G round)
         auto release_q = [&](const Item& it, int qs) {
@@ -274,17 +278,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         cur.set(descs[0]);
         tc_fence_after();
         if (g == 0) issue_g(cur, 0, 0);
-        issue_s_first(cur, 0);
+        if (g < cur.n_kv) {
+            issue_s_first(cur, 0, e);
+            ++e;
+        }
         int n = 0;
         for (int item = blockIdx.x;; item += gridDim.x, ++n) {
             const int qs = n & 1;
             const bool has_next = item + (int)gridDim.x < n_items;
-            if (g == 0 && cur.nc16 > G_ROUND1) {       // second G round over the first 64 columns, once they are drained
+            if (g == 0 && cur.nc16 > G_ROUND1) {       // second G round over the first 128 columns, once they are drained
                 bar_wait(smem_u32(&bars->g_lo_free), (uint32_t)(n & 1), 206);
                 tc_fence_after();
                 issue_g(cur, qs, 1);
             }
-            bool ga_seen = false;
+            bool ga_seen = false, next_first_done = false;
             // after this warp's last S of the item: release Q, look at the next item, (group 0) issue its G
             auto after_last_s = [&]() {
                 release_q(cur, qs);
@@ -299,28 +306,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 if (g == 0) issue_g(nxt, qs ^ 1, 0);
             };
             if (g + 2 >= cur.n_kv) after_last_s();      // the pre-issued S was this warp's only one
-            for (int j = g; j < cur.n_kv; j += 2, ++e, ++cnt) {
+            for (int j = g; j < cur.n_kv; j += 2, ++e, ++n_pv) {
                 const int slot = e % NS;
-                bar_wait(pfull, cnt & 1, 208);
                 bar_wait(kvf + slot * 8, (e / NS) & 1, 203);
+                // ---- the next S of this group goes out first: it only needs the S buffer (read early in the block) ----------
+                if (j + 2 < cur.n_kv) {
+                    issue_s(cur, qs, j + 2, slot);
+                    if (j + 4 >= cur.n_kv) after_last_s();
+                } else if (has_next && g < nxt.n_kv) {       // ... across the item boundary too (lone-K entry e + 1)
+                    issue_s_first(nxt, qs ^ 1, e + 1);
+                    next_first_done = true;
+                }
+                // ---- O_g += P_j V_j ---------------------------------------------------------------------------------------------
+                bar_wait(pfull, n_pv & 1, 208);
                 tc_fence_after();
                 const uint64_t dv = umma_desc_sw128_mnmajor(ring + slot * ENTRY_B);
                 const int valid = cur.klen(j);
                 const uint32_t acc0 = j >= 2 ? 1u : 0u;
                 if (valid >= FK) {           // full block: four K = 16 steps, 16 V rows (2048 B) each
                     if (elect_one()) {
-                        umma_bf16_ts(d_o, d_s, dv, idesc_o, acc0);
+                        umma_bf16_ts(d_o, d_p, dv, idesc_o, acc0);
 #pragma unroll
-                        for (int k = 1; k < 4; ++k) umma_bf16_ts(d_o, d_s + k * 8, dv + (uint64_t)(k * 128), idesc_o, 1u);
+                        for (int k = 1; k < 4; ++k) umma_bf16_ts(d_o, d_p + k * 8, dv + (uint64_t)(k * 128), idesc_o, 1u);
+                        umma_commit(pvdone);
+                        umma_commit(kve + slot * 8);
                     }
                 } else {
                     const int ks = (valid + 15) >> 4;
-                    if (elect_one())
-                        for (int k = 0; k < ks; ++k) umma_bf16_ts(d_o, d_s + k * 8, dv + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : acc0);
+                    if (elect_one()) {
+                        for (int k = 0; k < ks; ++k) umma_bf16_ts(d_o, d_p + k * 8, dv + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : acc0);
+                        umma_commit(pvdone);
+                        umma_commit(kve + slot * 8);
+                    }
                 }
-                if (j + 2 < cur.n_kv) issue_s(cur, qs, j + 2, slot);
-                if (elect_one()) umma_commit(kve + slot * 8);
-                if (j + 2 < cur.n_kv && j + 4 >= cur.n_kv) after_last_s();
             }
             // o_full needs both groups' last P.V; it may only complete once every softmax thread has seen the previous
             // item's o_full (ga_empty), so a waiter is never lapped by two phases
@@ -330,7 +348,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 else mbar_arrive(smem_u32(&bars->o_full));
             }
             if (!has_next) break;
-            issue_s_first(nxt, qs ^ 1);
+            if (g < nxt.n_kv) {
+                if (!next_first_done) issue_s_first(nxt, qs ^ 1, e);
+                ++e;
+            }
             cur = nxt;
         }
     } else {
@@ -341,6 +362,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t t_s = t_lane + TM_S + g * FK;
         const uint32_t t_o = t_lane + TM_O + g * kHeadDim;
+        const uint32_t t_p = t_lane + TM_P + g * (FK / 2);
         __half* my_qt = reinterpret_cast<__half*>(smem_al + SM_QT) + row * QT_LD;
         float* xm = reinterpret_cast<float*>(smem_al + SM_XM);
         float* xl = reinterpret_cast<float*>(smem_al + SM_XL);
@@ -428,23 +450,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     *reinterpret_cast<uint4*>(dst + e) = o4;
                 }
             };
-            if (active && g < n_chunks) drain(g, g * 32);                  // chunks 0 / 1 first: round two reuses their columns
+            if (active)
+                for (int c = g; c < min(n_chunks, G_LO_CHUNKS); c += 2) drain(c, c * 32);     // round two reuses these columns
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->g_lo_free));
             if (active)
-                for (int c = g + 2; c < min(n_chunks, 8); c += 2) drain(c, c * 32);
+                for (int c = G_LO_CHUNKS + g; c < min(n_chunks, G_ROUND1 / 32); c += 2) drain(c, c * 32);
+
+            // ---- previous item's epilogue (its last P.V ran while the table was drained; the second G round runs now) ----
+            if (n > 0) epilogue();
+
             if (it.nc16 > G_ROUND1) {
                 bar_wait(smem_u32(&bars->g2_full), n_g2 & 1, 311);
                 ++n_g2;
                 tc_fence_after();
-                if (active && 8 + g < n_chunks) drain(8 + g, g * 32);
+                if (active)
+                    for (int c = G_ROUND1 / 32 + g; c < n_chunks; c += 2) drain(c, (c - G_ROUND1 / 32) * 32);
             }
             if (active) named_bar_sync(bar_id, 64);       // both column sets of my rows are in place
-
-            // ---- previous item's epilogue (its last P.V ran while the table was drained) ---------------------------------
-            if (n > 0) epilogue();
-            // G has left TMEM -- and this thread has seen o_full of the previous item, so o_full (which the MMA warp only
-            // completes for item n after this barrier) can never run two phases ahead of a waiter
+            // G has left TMEM -- and this thread has seen o_full of the previous item, so o_full (which the MMA warps only
+            // complete for item n after this barrier) can never run two phases ahead of a waiter
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->ga_empty));
 
@@ -455,7 +480,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             for (int j = g; j < it.n_kv; j += 2, ++cnt) {
                 const int j0 = it.k0(j), jlen = it.klen(j);
                 const int nch = active ? (jlen + 31) >> 5 : 0;      // 32-key chunks that hold keys
-                bar_wait(smem_u32(&bars->s_full[g]), cnt & 1, 312);      // also: this group's previous P.V has completed
+                bar_wait(smem_u32(&bars->s_full[g]), cnt & 1, 312);
                 tc_fence_after();
                 uint32_t su[2][32];                // scores, fp32 bit patterns (one array from the TMEM load to the exponentials)
                 if (nch > 0) tmem_ld_32x32(t_s, su[0]);
@@ -465,6 +490,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int e = 0; e < 32; ++e) asm volatile("" : "+r"(su[c][e]));
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars->s_empty[g]));     // the group's next S may be written
 #define SC(c, e) __uint_as_float(su[c][e])
 #define SET_SC(c, e, v) su[c][e] = __float_as_uint(v)
                 float cbias[2] = {0.f, 0.f};       // per-chunk scalar bias (clamped regions), folded into the exp argument
@@ -503,6 +530,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     }
                     mloc = fmaxf(mloc, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) + cbias[c]);
                 }
+                if (cnt > 0) {          // P_g and O_g are free once this group's previous P.V has completed (issued a block ago)
+                    bar_wait(smem_u32(&bars->pv_done[g]), (cnt - 1) & 1, 314);
+                    tc_fence_after();
+                }
                 if (active && __any_sync(0xffffffffu, mloc > row_max + kLazyRescale)) {
                     const float mx = fmaxf(row_max, mloc);
                     const float corr = ex2_approx(row_max - mx);      // first block: exp2(-inf) = 0
@@ -535,7 +566,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                         ps[(e >> 1) & 1] = add_f32x2(ps[(e >> 1) & 1], p);
                         pp[e >> 1] = pack_bf16(p.x, p.y);
                     }
-                    tmem_st_32x16(t_s + c * 16, pp);
+                    tmem_st_32x16(t_p + c * 16, pp);
                 }
                 row_sum += (ps[0].x + ps[0].y) + (ps[1].x + ps[1].y);
                 tmem_st_wait();
