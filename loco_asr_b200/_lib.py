@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libloco_asr.so")
+LIB_PATH = os.environ.get("LOCO_ASR_LIB") or os.path.join(_HERE, "libloco_asr.so")   # env override: A/B builds in tools/
 CSRC = os.path.join(_HERE, "csrc")
 
 LOCO_F32, LOCO_F16, LOCO_BF16, LOCO_F64 = 0, 1, 2, 3

@@ -5,33 +5,43 @@
 //   ctx_i   = sum_j softmax_j(S[i, :]) v_j        over the keys of the SAME utterance only
 //
 // Persistent, warp-specialised: one CTA per SM walks a list of work items (128-query tile x head of one utterance).
-// pe_k (40 KB) is TMA-loaded once per CTA and stays in shared memory; Q tiles (2 slots) and 64-key K / V blocks (8-slot
-// ring) stream in through TMA in 32-row boxes, so a short utterance moves only the rows it has.  One thread issues every
-// MMA (TMEM columns in brackets):
-//   G   = Q pe_k^T         128 x (table columns this tile can reach, <= 320)  [256, 512); columns past 256 in a second round
-//   S_j = Q K_j^T          128 x 64 (N trimmed to the keys that exist)         [0, 64) even j, [64, 128) odd j
-//   O_g += P_j V_j         128 x 64 per block parity g                         [128, 192) / [192, 256)
-//                          A operand P_j is read FROM TMEM (bf16 pairs written by tcgen05.st over the first 32 columns of
-//                          S_j), V_j is the MN-major B operand exactly as TMA laid it out ([key][dim])
+// pe_k (40 KB) is TMA-loaded once per CTA and stays in shared memory; Q tiles (2 slots) and 64-key K / V blocks (a 2-entry
+// ring per softmax group, entry = V_j | K_{j+2}) stream in through TMA in 32-row boxes, so a short utterance moves only
+// the rows it has.  TMEM map (512 columns):
+//   S_g   = Q K_j^T        128 x 64 (N trimmed to the keys that exist)      [0, 64) group 0, [64, 128) group 1
+//   P_g   bf16 pairs written by tcgen05.st, read back as the A operand      [128, 160) / [160, 192)
+//   O_g  += P_j V_j        128 x 64; V_j is the MN-major B operand ([key][dim] exactly as TMA laid it out)   [192, 320)
+//   G     = Q pe_k^T       128 x (table columns this tile can reach, <= 320) [320, 512): 192 columns, the rest in a second
+//                          round over the first 128 columns once those are drained
 // G is drained once per item into an fp16 table in shared memory (row i of the tile = row of the table), because the
 // bias of key j sits at the per-row offset i - j + 160 -- a skew no TMEM load shape can express.  The reference's
 // [T, T, 64] position_bias (575 MB at 30 s) and the T x T score matrix never exist.
 //
-// Two softmax groups of four warps ping-pong over the key blocks: group g takes blocks j = g, g+2, ... with one query
-// row per thread (TMEM lane == row), its own score buffer, running maximum, row sum and O accumulator, so the groups
-// never talk inside an item and one runs its exponentials (MUFU) while the other adds bias / takes maxima (LSU, ALU)
-// or waits for its next S.  The running maximum is only raised when some row of the warp would exceed it by more than
-// 2^8 (P stays <= 256), so the O rescale in TMEM is rare.  At the end of an item the two partial results are merged:
+// Twelve warps.  Two softmax groups of four warps ping-pong over the key blocks: group g takes blocks j = g, g+2, ... with
+// one query row per thread (TMEM lane == row), its own S / P / O buffers, running maximum and row sum, so the groups never
+// talk inside an item and one runs its exponentials (MUFU) while the other adds bias / takes maxima (LSU, ALU).  Each
+// group has its own TMA loader warp and MMA issuer warp (group 0's also issues G and loads Q / pe_k): with 32-cycle MMAs
+// (N = 64) a single issuing thread was the bottleneck (ncu: softmax warps 50 % in the s_full wait, MMA warp never idle).
+// The issuer runs warp-uniform control flow with one elected lane, so descriptors stay in uniform registers.  S_{j+2} is
+// issued as soon as the group has read S_j out of TMEM (s_empty), long before P_j exists, so the tensor round trip is off
+// the critical path.  The running maximum is only raised when some row of the warp would exceed it by more than 2^8 (P stays
+// <= 256), so the O rescale in TMEM is rare.  At the end of an item the two partial results are merged:
 //   O = (2^(m_a - m) O_a + 2^(m_b - m) O_b) / (2^(m_a - m) l_a + 2^(m_b - m) l_b).
 // Per score: LDS.U16 + FHADD (bias), FMNMX3, FADD2, MUFU.EX2, FADD2, F2FP -- about 5 issue slots.
 //
-// Items overlap: G_{n+1} is issued as soon as item n's last S is, S_{n+1,0/1} right after item n's last P.V; the softmax
-// warps drain G_{n+1} into the table and only then run item n's epilogue, hiding the last P.V behind the drain.
+// Items overlap: G_{n+1} is issued as soon as item n's last S is, S_{n+1,g} as soon as the group has read its last S of item
+// n; the softmax warps drain G_{n+1} into the table and run item n's epilogue in between, hiding its last P.V and the
+// second G round.
 //
-// mbarriers: pe_full; per item q_full[2]/q_empty[2] (slot n & 1), g_full, g_lo_free (first 64 G columns drained, 256
-// arrivals), g2_full (second G round), ga_empty (table complete, 256 arrivals), o_full; per K or V block
-// ring entry kv_full[4]/kv_empty[4]; per key block and group s_full[g], p_full[g] (128 arrivals).  Every softmax thread runs the
-// same barrier skeleton whether or not its rows exist.
+// mbarriers: pe_full; per item q_full[2]/q_empty[2] (slot n & 1; 2 arrivals: both MMA warps), g_full, g_lo_free (first 128 G
+// columns drained, 256 arrivals), g2_full, ga_empty (table complete and previous o_full seen, 256 arrivals), o_full (2
+// arrivals); per group and ring entry kv_full/kv_empty; per group and key block s_full, s_empty (128), p_full (128),
+// pv_done.  Every softmax thread runs the same barrier skeleton whether or not its rows exist, and no waiter can be lapped
+// by two phases of its barrier (see ga_empty / o_full).  Set LOCO_ATTN_DEBUG=1 to have a stuck wait reported per role.
+//
+// Measured (tools/attn_sweep.py, 64k frames per batch, per layer): 0.36 ms at T = 256, 0.51 ms at 499, 0.95 ms at 1499,
+// 1.59 ms at 2999 (384 TFLOP/s of Q K^T + P V + table FLOPs) -- 1.5-1.95x the mma.sync kernel; below ~176 frames the
+// per-item fixed costs (drain, epilogue, ~10 barrier hand-offs) dominate and the mma.sync kernel (attention.cu) is used.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 

@@ -212,10 +212,9 @@ __global__ void __launch_bounds__(C0_WARPS * 32) conv0_mma_kernel(const float* _
             }
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                *reinterpret_cast<uint32_t*>(my_stage + gq * C0_SLD + n * 8 + tq * 2) =
-                    pack_bf16(gelu_erf(acc[n][0]), gelu_erf(acc[n][1]));
-                *reinterpret_cast<uint32_t*>(my_stage + (gq + 8) * C0_SLD + n * 8 + tq * 2) =
-                    pack_bf16(gelu_erf(acc[n][2]), gelu_erf(acc[n][3]));
+                const float2 g0 = gelu_erf2(make_float2(acc[n][0], acc[n][1])), g1 = gelu_erf2(make_float2(acc[n][2], acc[n][3]));
+                *reinterpret_cast<uint32_t*>(my_stage + gq * C0_SLD + n * 8 + tq * 2) = pack_bf16(g0.x, g0.y);
+                *reinterpret_cast<uint32_t*>(my_stage + (gq + 8) * C0_SLD + n * 8 + tq * 2) = pack_bf16(g1.x, g1.y);
             }
             __syncwarp();
 #pragma unroll

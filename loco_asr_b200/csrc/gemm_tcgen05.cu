@@ -29,7 +29,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+// 4 smem stages and one staging panel per epilogue warp.  (A 3-stage / two-panel variant that prefetches both residual
+// panels of a tile while its MMAs run was measured and lost: out_proj 977 -> 896, FFN2 1278 -> 1185 TFLOP/s in
+// tools/gemm_sweep.py -- the fourth operand stage is worth more than hiding the residual round trip.)
+template <int EPI> struct GemmCfg {
+    static constexpr int STAGES = 4;
+    static constexpr int PANELS = 1;
+};
+constexpr int MAX_STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -38,11 +45,13 @@ constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int PANEL_BYTES = 32 * 128;       // one epilogue warp's staging panel: 32 rows x 64 bf16
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * PANEL_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+template <int EPI> constexpr int smem_bytes() {
+    return GemmCfg<EPI>::STAGES * STAGE_BYTES + GemmCfg<EPI>::PANELS * NUM_EPI_WARPS * PANEL_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+}
 
 struct __align__(8) Barriers {
-    uint64_t full[STAGES];
-    uint64_t empty[STAGES];
+    uint64_t full[MAX_STAGES];
+    uint64_t empty[MAX_STAGES];
     uint64_t tmem_full[ACC_STAGES];
     uint64_t tmem_empty[ACC_STAGES];
     uint64_t res_full[NUM_EPI_WARPS];   // residual panel landed (one per epilogue warp)
@@ -54,10 +63,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
                const float* __restrict__ bias, int M, int N, int K) {
+    constexpr int STAGES = GemmCfg<EPI>::STAGES, PANELS = GemmCfg<EPI>::PANELS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-    Barriers* bars = reinterpret_cast<Barriers*>(smem_aligned + STAGES * STAGE_BYTES + NUM_EPI_WARPS * PANEL_BYTES);
+    Barriers* bars = reinterpret_cast<Barriers*>(smem_aligned + STAGES * STAGE_BYTES + PANELS * NUM_EPI_WARPS * PANEL_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -142,8 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // ===================== epilogue: TMEM -> registers -> swizzled smem panel -> TMA store ==============
         const int q = warp & 3;             // TMEM lane quadrant this warp may access
         const int half = (warp - 4) >> 2;   // which 128 of the tile's 256 columns
-        const uint32_t panel = smem_base + STAGES * STAGE_BYTES + (warp - 4) * PANEL_BYTES;
-        const uint32_t my_row = panel + lane * 128;      // this thread's accumulator row inside the panel
+        const uint32_t panel0 = smem_base + STAGES * STAGE_BYTES + (warp - 4) * PANELS * PANEL_BYTES;
         const uint32_t res_bar = smem_u32(&bars->res_full[warp - 4]);
         uint32_t res_phase = 0;
         int acc = 0;
@@ -151,14 +160,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles_n) * BM + q * 32;
             const int n0 = (tile % n_tiles_n) * BN + half * (BN / 2);
+            if (EPI == EPI_BIAS_RESIDUAL && PANELS == 2) {
+                // both residual panels of this warp's 32 x 128 slice, fetched while the tile's MMAs still run
+                if (lane == 0) {
+                    bulk_wait_read<0>();            // the previous tile's stores have finished reading the panels
+                    mbar_arrive_expect_tx(res_bar, 2 * PANEL_BYTES);
+                    tma_load_2d(panel0, &tma_r, res_bar, n0, m0);
+                    tma_load_2d(panel0 + PANEL_BYTES, &tma_r, res_bar, n0 + 64, m0);
+                }
+                __syncwarp();
+            }
             mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
             uint32_t v[2][32];
             tmem_ld_32x32(t_row, v[0]);
+            if (EPI == EPI_BIAS_RESIDUAL && PANELS == 2) {
+                mbar_wait(res_bar, res_phase);
+                res_phase ^= 1u;
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {           // 4 chunks of 32 columns = 2 panels of 64
-                if ((c & 1) == 0) {
+                const uint32_t panel = panel0 + (PANELS == 2 ? (c >> 1) * PANEL_BYTES : 0);
+                const uint32_t my_row = panel + lane * 128;      // this thread's accumulator row inside the panel
+                if (PANELS == 1 && (c & 1) == 0) {
                     // the previous TMA store must have finished reading the panel before it is overwritten
                     if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
@@ -175,39 +200,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     tc_fence_before();
                     mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
                 }
-                if (EPI == EPI_BIAS_RESIDUAL && (c & 1) == 0) {
+                if (EPI == EPI_BIAS_RESIDUAL && PANELS == 1 && (c & 1) == 0) {
                     mbar_wait(res_bar, res_phase);
                     res_phase ^= 1u;
                 }
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
-                    float f[8];
+                    float2 f[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c & 1][j + e]);
+                    for (int e = 0; e < 4; ++e) f[e] = make_float2(__uint_as_float(v[c & 1][j + 2 * e]), __uint_as_float(v[c & 1][j + 2 * e + 1]));
                     if (bias != nullptr) {
                         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j));
                         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j + 4));
-                        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        f[0] = add_f32x2(f[0], make_float2(b0.x, b0.y));
+                        f[1] = add_f32x2(f[1], make_float2(b0.z, b0.w));
+                        f[2] = add_f32x2(f[2], make_float2(b1.x, b1.y));
+                        f[3] = add_f32x2(f[3], make_float2(b1.z, b1.w));
                     }
                     if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+                        for (int e = 0; e < 4; ++e) f[e] = gelu_erf2(f[e]);
                     }
                     // 16-byte chunk k of row r sits at r*128 + ((k ^ (r & 7)) * 16) under SWIZZLE_128B
                     const uint32_t addr = my_row + ((((c & 1) * 4 + (j >> 3)) ^ (lane & 7)) << 4);
                     if (EPI == EPI_BIAS_RESIDUAL) {
                         const uint4 rr = lds128(addr);
-                        const float2 r0 = unpack_bf16(rr.x), r1 = unpack_bf16(rr.y), r2 = unpack_bf16(rr.z),
-                                     r3 = unpack_bf16(rr.w);
-                        f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
-                        f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+                        f[0] = add_f32x2(f[0], unpack_bf16(rr.x));
+                        f[1] = add_f32x2(f[1], unpack_bf16(rr.y));
+                        f[2] = add_f32x2(f[2], unpack_bf16(rr.z));
+                        f[3] = add_f32x2(f[3], unpack_bf16(rr.w));
                     }
                     uint4 o;
-                    o.x = pack_bf16(f[0], f[1]);
-                    o.y = pack_bf16(f[2], f[3]);
-                    o.z = pack_bf16(f[4], f[5]);
-                    o.w = pack_bf16(f[6], f[7]);
+                    o.x = pack_bf16(f[0].x, f[0].y);
+                    o.y = pack_bf16(f[1].x, f[1].y);
+                    o.z = pack_bf16(f[2].x, f[2].y);
+                    o.w = pack_bf16(f[3].x, f[3].y);
                     sts128(addr, o);
                 }
                 if (c & 1) {
@@ -252,7 +279,7 @@ int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, 
 template <int EPI>
 int launch_t(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr,
              int grid, cudaStream_t stream) {
-    gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mc, mr, g.bias, g.M, g.N, g.K);
+    gemm_tc_kernel<EPI><<<grid, NUM_THREADS, smem_bytes<EPI>(), stream>>>(ma, mb, mc, mr, g.bias, g.M, g.N, g.K);
     return (int)cudaGetLastError();
 }
 
@@ -273,11 +300,11 @@ int gemm_tc_init() {
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
     cudaError_t e;
-    e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI_BIAS>());
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI_BIAS_GELU>());
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI_BIAS_RESIDUAL>());
     return (int)e;
 }
 

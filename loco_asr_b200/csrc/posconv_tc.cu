@@ -143,15 +143,17 @@ posconv_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w, const 
                 if (ok) {
 #pragma unroll
                     for (int j8 = 0; j8 < 16; j8 += 8) {
-                        float f[8];
+                        float2 f[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            f[e] = gelu_erf(__uint_as_float(v[j8 + e]) + __ldg(bias + g * kPosGroupCh + c * 16 + j8 + e));
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + g * kPosGroupCh + c * 16 + j8 + 2 * e));
+                            f[e] = gelu_erf2(add_f32x2(make_float2(__uint_as_float(v[j8 + 2 * e]), __uint_as_float(v[j8 + 2 * e + 1])), b2));
+                        }
                         uint4 o4;
-                        o4.x = pack_bf16(f[0], f[1]);
-                        o4.y = pack_bf16(f[2], f[3]);
-                        o4.z = pack_bf16(f[4], f[5]);
-                        o4.w = pack_bf16(f[6], f[7]);
+                        o4.x = pack_bf16(f[0].x, f[0].y);
+                        o4.y = pack_bf16(f[1].x, f[1].y);
+                        o4.z = pack_bf16(f[2].x, f[2].y);
+                        o4.w = pack_bf16(f[3].x, f[3].y);
                         *reinterpret_cast<uint4*>(orow + c * 16 + j8) = o4;
                     }
                 }
