@@ -166,7 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             mbar_init(smem_u32(&bars->s_empty[s]), FA_SOFTMAX_WARPS * 16);
             mbar_init(smem_u32(&bars->pv_done[s]), 1);
             mbar_init(smem_u32(&bars->q_full[s]), 1);
-            mbar_init(smem_u32(&bars->q_empty[s]), 2);
+            mbar_init(smem_u32(&bars->q_empty[s]), 2 + FA_SOFTMAX_WARPS);     // both MMA warps + every softmax warp's epilogue
         }
         for (int s = 0; s < 2 * NS; ++s) {
             mbar_init(smem_u32(&bars->kv_full[0][s]), 1);
@@ -379,15 +379,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         const int bar_id = 1 + q;
 
         // deferred epilogue state (previous item)
-        bool prev_active = false, prev_store = false, prev_two = false;
-        bf16* prev_out = nullptr;
+        bool prev_active = false, prev_two = false;
+        int prev_nr = 0;
+        bf16* prev_out = nullptr;                  // first row of the item's tile, this head's 64 columns
         uint32_t cnt = 0;                          // key blocks this group has seen (parity of s_full[g])
         uint32_t n_g2 = 0;                         // items that needed a second G round
 
         int n = 0;
-        auto epilogue = [&]() {                    // item n - 1
+        // Item n - 1's result: merge the two groups' partial accumulators, stage the 128 x 64 bf16 tile in the item's own Q
+        // slot (its MMAs are done once o_full has completed; the loader refills the slot only after this epilogue has
+        // arrived on q_empty) and write it out with full 128-byte lines per row.  Storing straight from the one-row-per-thread
+        // registers touched 32 different lines per instruction and cost ~2 us per item on the LSU (a third of the kernel at
+        // 2-3 s utterances).
+        auto epilogue = [&]() {
             bar_wait(smem_u32(&bars->o_full), (uint32_t)((n - 1) & 1), 309);
             tc_fence_after();
+            const uint32_t stage = sbase + SM_Q + ((n - 1) & 1) * Q_TILE_B;
             if (prev_active) {
                 const float ma = xm[row], mb = xm[FQ + row];
                 const float m = fmaxf(ma, mb);
@@ -413,21 +420,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
 #pragma unroll
                         for (int e = 0; e < 16; ++e) o[e] = fmaf(__uint_as_float(vb[e]), wb, o[e]);
                     }
-                    if (prev_store) {
 #pragma unroll
-                        for (int e = 0; e < 16; e += 8) {
-                            uint4 o4;
-                            o4.x = pack_bf16(o[e + 0], o[e + 1]);
-                            o4.y = pack_bf16(o[e + 2], o[e + 3]);
-                            o4.z = pack_bf16(o[e + 4], o[e + 5]);
-                            o4.w = pack_bf16(o[e + 6], o[e + 7]);
-                            *reinterpret_cast<uint4*>(prev_out + hh * 16 + e) = o4;
-                        }
+                    for (int e = 0; e < 16; e += 8) {
+                        uint4 o4;
+                        o4.x = pack_bf16(o[e + 0], o[e + 1]);
+                        o4.y = pack_bf16(o[e + 2], o[e + 3]);
+                        o4.z = pack_bf16(o[e + 4], o[e + 5]);
+                        o4.w = pack_bf16(o[e + 6], o[e + 7]);
+                        const int chunk = g * 4 + hh * 2 + (e >> 3);        // 16-byte chunk of the row's 128-byte line
+                        sts128(stage + row * 128 + ((chunk ^ (row & 7)) << 4), o4);
                     }
                 }
                 tc_fence_before();
-                named_bar_sync(bar_id, 64);       // both groups have read both accumulators before either P.V restarts them
+                named_bar_sync(bar_id, 64);       // both halves of the quad's rows are staged, and both groups have read both
+                                                  // accumulators before either P.V restarts them
+                // warp (q, g) writes rows 32 q + 16 g + [0, 16): 8 lanes per row, 4 full lines per instruction
+#pragma unroll
+                for (int r4 = 0; r4 < 4; ++r4) {
+                    const int r = q * 32 + g * 16 + r4 * 4 + (lane >> 3), chunk = lane & 7;
+                    if (r < prev_nr) {
+                        const uint4 o4 = lds128(stage + r * 128 + ((chunk ^ (r & 7)) << 4));
+                        *reinterpret_cast<uint4*>(prev_out + (int64_t)r * kHidden + chunk * 8) = o4;
+                    }
+                }
             }
+            fence_proxy_async_smem();             // generic accesses to the slot are ordered before the TMA refill
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->q_empty[(n - 1) & 1]));
         };
 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
@@ -590,9 +609,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             if (active) {
                 xm[g * FQ + row] = row_max;
                 xl[g * FQ + row] = row_sum;
-                prev_store = i < it.T;
+                prev_nr = it.nr;
                 prev_two = it.n_kv > 1;
-                prev_out = ctx + (int64_t)(it.row0 + row) * kHidden + it.head * kHeadDim + g * 32;
+                prev_out = ctx + (int64_t)it.row0 * kHidden + it.head * kHeadDim;
             }
         }
         if (n > 0) {
