@@ -252,12 +252,21 @@ def main():
             fl["pos_conv"] += d["pos_conv"]
             fl["total"] += d["total"]
     gemm_ms, gemm_n = prof["gemm"]
+    # DRAM bytes per GEMM launch come from the committed ncu capture of the same command (profiles/), never from this run
+    gemm_traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01c_gemm_traffic.json")) as fh:
+            tj = json.load(fh)
+        gemm_traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     achieved = fl["gemm"] / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak = peaks["tflops_sustained"]
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMEM/TMA bf16 GEMM, all epilogues)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                "traffic": None, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                "traffic": gemm_traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)" if gemm_traffic else None,
+                "traffic_source": traffic_src, "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "algorithmic_flops_per_launch": fl["gemm"] / max(gemm_n, 1),
                 "share_of_step": gemm_ms / ms if ms else None}
     stage_ms = {k: round(v[0] / K, 4) for k, v in prof.items()}
