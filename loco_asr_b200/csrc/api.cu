@@ -43,6 +43,7 @@ struct Layout {
     std::vector<UttMeta> meta;
     std::vector<PcTile> pc_tiles;
     size_t off_pctiles = 0;
+    size_t off_at_tiles = 0, off_at_utts = 0;   // attention work lists: tcgen05 tiles / mma.sync utterance indices
     size_t off_meta = 0, off_partial = 0, off_scale = 0, off_shift = 0, off_rowframe = 0;
     std::map<std::string, Buf> bufs;
     size_t bytes = 0;
@@ -77,7 +78,8 @@ struct loco_handle {
     int gemm_impl = 0;
     int posconv_impl = 0;
     int attn_impl = -1;         // -1 = by length (tcgen05 from attn_tc_min_frames), 0 = tcgen05, 1 = mma.sync
-    int attn_tc_min_frames = 176;
+    int attn_tc_min_frames = 193;   // utterances with at least this many frames use the tcgen05 attention kernel,
+    int attn_tc_lo = 84, attn_tc_hi = 128;   // ... and so do utterances that fill most of one 128-query tile (see loco_encode)
     alignas(64) CUtensorMap pe_map;   // pe_k [320, 64] for the tcgen05 attention kernel
     int stop_after_layer = -1;
     Layout last;
@@ -268,6 +270,8 @@ int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L)
     };
     L->off_meta = take((size_t)n_utts * sizeof(UttMeta));
     L->off_pctiles = take(L->pc_tiles.size() * sizeof(PcTile));
+    L->off_at_tiles = take(L->pc_tiles.size() * sizeof(PcTile));
+    L->off_at_utts = take((size_t)n_utts * sizeof(int32_t));
     L->off_partial = take((size_t)n_utts * L->chunks * 65 * sizeof(double));
     L->off_scale = take((size_t)n_utts * kConvDim * sizeof(float));
     L->off_shift = take((size_t)n_utts * kConvDim * sizeof(float));
@@ -626,6 +630,30 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
     CK(cudaMemcpyAsync(meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta), cudaMemcpyHostToDevice, s));
     PcTile* pc_tiles = reinterpret_cast<PcTile*>(ws + L.off_pctiles);
     CK(cudaMemcpyAsync(pc_tiles, L.pc_tiles.data(), L.pc_tiles.size() * sizeof(PcTile), cudaMemcpyHostToDevice, s));
+    // ---- attention work lists.  The kernel is chosen PER UTTERANCE by its own frame count, never by its batch-mates, so
+    // an utterance's result does not depend on the batch it travels in.  Measured with tools/attn_sweep.py (ms per layer
+    // at 64k frames, tcgen05 / mma.sync): 64 frames 0.33 / 0.20, 96: 0.26 / 0.28, 128: 0.25 / 0.31, 136: 0.50 / 0.41,
+    // 192: 0.44 / 0.38, 224: 0.40 / 0.54, 499: 0.51 / 0.85, 2999: 1.56 / 3.10.  The persistent tcgen05 kernel pays a fixed
+    // cost per 128-query tile, so it loses where the second tile is mostly empty (129..192 frames) and on very short
+    // utterances; the mma.sync kernel works in 64-query tiles, 3-4 CTAs/SM.
+    std::vector<PcTile> at_tiles;
+    std::vector<int32_t> at_utts;
+    int at_ms_max_t6 = 0;
+    for (int u = 0; u < n_utts; ++u) {
+        const int t6 = L.meta[u].t6;
+        const bool tc = h->attn_impl == 0 ||
+                        (h->attn_impl < 0 && (t6 >= h->attn_tc_min_frames || (t6 >= h->attn_tc_lo && t6 <= h->attn_tc_hi)));
+        if (tc) {
+            for (int f = 0; f < t6; f += 128) at_tiles.push_back({L.meta[u].row6 + f, f, t6, 0});
+        } else {
+            at_utts.push_back(u);
+            if (t6 > at_ms_max_t6) at_ms_max_t6 = t6;
+        }
+    }
+    PcTile* at_tiles_dev = reinterpret_cast<PcTile*>(ws + L.off_at_tiles);
+    int32_t* at_utts_dev = reinterpret_cast<int32_t*>(ws + L.off_at_utts);
+    if (!at_tiles.empty()) CK(cudaMemcpyAsync(at_tiles_dev, at_tiles.data(), at_tiles.size() * sizeof(PcTile), cudaMemcpyHostToDevice, s));
+    if (!at_utts.empty()) CK(cudaMemcpyAsync(at_utts_dev, at_utts.data(), at_utts.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     for (int i = 0; i < 6; ++i) {  // the 8 pad frames the last implicit-GEMM rows of layer i+1 may touch
         char nm[16];
         snprintf(nm, sizeof nm, "conv%d", i);
@@ -684,12 +712,10 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         g.A = B("x"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wqkv; g.C = B("qkv"); g.ldc = 3 * kHidden;
         g.bias = w.bqkv; g.M = R6; g.N = 3 * kHidden; g.K = kHidden; g.epilogue = EPI_BIAS;
         if ((rc = run_gemm(h, g, s))) return rc;
-        // both kernels are product paths, chosen by shape: the mma.sync kernel wins on short utterances (64-row tiles, 3-4
-        // CTAs/SM), the tcgen05 kernel on long ones (128 x 128 blocks, MMA off the issue slots)
-        if (h->attn_impl == 1 || (h->attn_impl < 0 && L.max_t6 < h->attn_tc_min_frames))
-            LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, n_utts, L.max_t6, B("ctx"), s), 1);
-        else
-            LAUNCH(CAT_ATTENTION, launch_attention_tc(&qkv_map, &h->pe_map, pc_tiles, (int)L.pc_tiles.size(), B("ctx"), h->num_sms, s), 1);
+        if (!at_utts.empty())
+            LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, at_utts_dev, (int)at_utts.size(), at_ms_max_t6, B("ctx"), s), 1);
+        if (!at_tiles.empty())
+            LAUNCH(CAT_ATTENTION, launch_attention_tc(&qkv_map, &h->pe_map, at_tiles_dev, (int)at_tiles.size(), B("ctx"), h->num_sms, s), 1);
         g = GemmArgs();
         g.A = B("ctx"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wo; g.C = B("attn_res"); g.ldc = kHidden;
         g.bias = w.bo; g.R = B("x"); g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kHidden; g.epilogue = EPI_BIAS_RESIDUAL;
@@ -789,6 +815,8 @@ int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
     else if (!strcmp(name, "posconv_impl")) h->posconv_impl = (int)value;
     else if (!strcmp(name, "attn_impl")) h->attn_impl = (int)value;
     else if (!strcmp(name, "attn_tc_min_frames")) h->attn_tc_min_frames = (int)value;
+    else if (!strcmp(name, "attn_tc_lo")) h->attn_tc_lo = (int)value;
+    else if (!strcmp(name, "attn_tc_hi")) h->attn_tc_hi = (int)value;
     else if (!strcmp(name, "stop_after_layer")) h->stop_after_layer = (int)value;
     else return fail(h, LOCO_ERR_INVALID, std::string("unknown debug knob: ") + name);
     return LOCO_OK;

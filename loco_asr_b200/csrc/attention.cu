@@ -51,8 +51,9 @@ __device__ __forceinline__ void load_tile32(bf16* dst, const bf16* src, int64_t 
 }
 
 __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ pe_k,
-                                                        const UttMeta* __restrict__ meta, bf16* __restrict__ ctx, int qt_cols) {
-    const UttMeta m = meta[blockIdx.z];
+                                                        const UttMeta* __restrict__ meta, const int32_t* __restrict__ utt_index,
+                                                        bf16* __restrict__ ctx, int qt_cols) {
+    const UttMeta m = meta[utt_index != nullptr ? utt_index[blockIdx.z] : (int)blockIdx.z];
     const int T = m.t6;
     const int i0 = blockIdx.x * AQ;
     if (i0 >= T) return;
@@ -303,11 +304,12 @@ int attention_init() {
     return (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(kRelCols));
 }
 
-int launch_attention(const bf16* qkv, const bf16* pe_k, const UttMeta* meta, int n_utts, int max_t6, bf16* ctx, cudaStream_t s) {
+int launch_attention(const bf16* qkv, const bf16* pe_k, const UttMeta* meta, const int32_t* utt_index, int n_utts, int max_t6, bf16* ctx,
+                     cudaStream_t s) {
     if (n_utts <= 0 || max_t6 <= 0) return 0;
     const int qt_cols = qt_cols_for(max_t6);
     dim3 grid((max_t6 + AQ - 1) / AQ, kHeads, n_utts);
-    attention_kernel<<<grid, 128, attn_smem_bytes(qt_cols), s>>>(qkv, pe_k, meta, ctx, qt_cols);
+    attention_kernel<<<grid, 128, attn_smem_bytes(qt_cols), s>>>(qkv, pe_k, meta, utt_index, ctx, qt_cols);
     return (int)cudaGetLastError();
 }
 
