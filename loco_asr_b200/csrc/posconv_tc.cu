@@ -99,29 +99,39 @@ posconv_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w, const 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(PT_ROWS, kPosGroupCh);
-            for (int it = 0; it < PT_N_ITERS; ++it) {
-                const int s = it % PT_STAGES;
-                const uint32_t ph = (uint32_t)(it / PT_STAGES) & 1u;
-                mbar_wait(smem_u32(&bars->full[s]), ph);
-                tc_fence_after();
-                for (int tap = 0; tap < PT_STAGE_TAPS; ++tap) {
-                    const int j = it * PT_STAGE_TAPS + tap;
-                    const uint32_t b_tap = ring_base + s * PT_STAGE_BYTES + tap * PT_TAP_BYTES;
-                    for (int t = 0; t < my_tiles; ++t) {
-                        const uint32_t a_tap = win_base + t * PT_WIN_BYTES + j * 16;
+        // MMA issuer.  Each MMA is only 128 x 48 x 16 (24 tensor-pipe cycles), so the issue path must be shorter than that:
+        // the whole warp runs the uniform control flow (descriptors stay in uniform registers; a single divergent lane paid
+        // an R2UR per operand and ~86 cycles per MMA -- 3.6x the tensor time, ncu r01c), one elected lane issues, and the
+        // descriptors are base values plus constants: tap j is +j, a K-step is +2 * 256 (A) or +2 * 48 (B) sixteen-byte units.
+        constexpr uint32_t idesc = umma_idesc_bf16(PT_ROWS, kPosGroupCh);
+        constexpr uint64_t kAStepK = (uint64_t)(2 * PT_WROWS);             // 2 core-matrix columns of the window, in 16 B units
+        constexpr uint64_t kBStepK = (uint64_t)(2 * kPosGroupCh);
+        constexpr uint64_t kBStepTap = (uint64_t)(PT_TAP_BYTES / 16);
+        const uint64_t da0 = umma_desc_noswizzle_kmajor(win_base, PT_WROWS * 16, 128);
+        const uint64_t db0 = umma_desc_noswizzle_kmajor(ring_base, kPosGroupCh * 16, 128);
+        for (int it = 0; it < PT_N_ITERS; ++it) {
+            const int s = it % PT_STAGES;
+            const uint32_t ph = (uint32_t)(it / PT_STAGES) & 1u;
+            mbar_wait(smem_u32(&bars->full[s]), ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t db_s = db0 + (uint64_t)(s * (PT_STAGE_BYTES / 16));
+                const uint64_t da_it = da0 + (uint64_t)(it * PT_STAGE_TAPS);
 #pragma unroll
-                        for (int kk = 0; kk < kPosGroupCh / 16; ++kk) {
-                            const uint64_t da = umma_desc_noswizzle_kmajor(a_tap + (2 * kk) * (PT_WROWS * 16), PT_WROWS * 16, 128);
-                            const uint64_t db = umma_desc_noswizzle_kmajor(b_tap + (2 * kk) * (kPosGroupCh * 16), kPosGroupCh * 16, 128);
-                            umma_bf16(tmem_base + t * 64, da, db, idesc, (j | kk) != 0 ? 1u : 0u);
-                        }
+                for (int tap = 0; tap < PT_STAGE_TAPS; ++tap) {
+                    const uint64_t db = db_s + tap * kBStepTap;
+                    for (int t = 0; t < my_tiles; ++t) {
+                        const uint64_t da = da_it + (uint64_t)(t * (PT_WIN_BYTES / 16) + tap);
+                        const uint32_t acc = (it | tap) != 0 ? 1u : 0u;
+                        umma_bf16(tmem_base + t * 64, da, db, idesc, acc);
+                        umma_bf16(tmem_base + t * 64, da + kAStepK, db + kBStepK, idesc, 1u);
+                        umma_bf16(tmem_base + t * 64, da + 2 * kAStepK, db + 2 * kBStepK, idesc, 1u);
                     }
                 }
                 umma_commit(smem_u32(&bars->empty[s]));
+                if (it == PT_N_ITERS - 1) umma_commit(smem_u32(&bars->done));
             }
-            umma_commit(smem_u32(&bars->done));
+            __syncwarp();
         }
     } else {
         // ---- epilogue: TMEM -> bias + GELU -> bf16 rows of pc ---------------------------------------------------
