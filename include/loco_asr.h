@@ -122,6 +122,23 @@ LOCO_API int loco_host_workspace_bytes(loco_handle* h, const int32_t* n_samples,
 LOCO_API int loco_encode_host(loco_handle* h, const float* wave_host, const int32_t* n_samples, int n_utts, float* pooled_host,
                      float* hidden_host, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- text modality (the `-m text` branch of the same scripts) ------------------------------------------------
+ * Replaces: out = model.speecht5.encoder(texts.input_ids) on SpeechT5ForTextToSpeech's encoder
+ * (extract_speecht5_base_embeddings_slurp.py:79-93) = SpeechT5EncoderWithTextPrenet (HF modeling_speecht5.py:1377-1415):
+ * SpeechT5TextEncoderPrenet (embed_tokens + scaled positional encoding, HF:765-779, 400-422) then the same SpeechT5Encoder.
+ * A handle serves this path when its state dict carried "prenet.embed_tokens.weight" [vocab, 768] and
+ * "prenet.encode_positions.alpha" (map_speecht5_hf.py:170-181; "prenet.encode_positions.pe" is accepted and ignored);
+ * speech and text prenet weights may be loaded into the same handle, the wrapped_encoder weights are shared.
+ *   n_tokens       i32[n_utts] (host)  tokens per text; each text is encoded alone, unpadded
+ *   tokens_dev     i32[sum n_tokens]   packed token ids (device); ids outside [0, vocab) are clamped
+ *   pooled_dev     f32[n_utts, 768]    mean of last_hidden_state over each text's own tokens
+ *   hidden_dev     f32[sum n_tokens, 768] or NULL
+ * loco_plan_text: rows[n_utts] = first row of text u in the stage buffers (== its offset in tokens_dev). */
+LOCO_API int loco_plan_text(loco_handle* h, const int32_t* n_tokens, int n_utts, int32_t* rows, int64_t* total_tokens,
+                            size_t* workspace_bytes);
+LOCO_API int loco_encode_text(loco_handle* h, const int32_t* tokens_dev, const int32_t* n_tokens, int n_utts, float* pooled_dev,
+                              float* hidden_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 LOCO_API int64_t loco_launch_count(const loco_handle* h);
 

@@ -73,6 +73,13 @@ struct loco_handle {
     int sin_rows = 0;
     float *eln_w = nullptr, *eln_b = nullptr;
     bf16* pe_k = nullptr;
+    // text prenet (SpeechT5TextEncoderPrenet): present when the state dict carried prenet.embed_tokens.weight
+    bool has_speech = false, has_text = false;
+    float* txt_embed = nullptr;   // [vocab, 768] fp32
+    int txt_vocab = 0;
+    float txt_alpha = 1.f;
+    float* txt_pe = nullptr;      // [txt_pe_rows, 768] fp32, SpeechT5ScaledPositionalEncoding table
+    int txt_pe_rows = 0;
     std::vector<LayerW> layers;
     // debug
     int gemm_impl = 0;
@@ -219,6 +226,79 @@ void conv_frames(const loco_config& c, int n_samples, int* t) {
         cur = cur >= c.conv_kernel[i] ? (cur - c.conv_kernel[i]) / c.conv_stride[i] + 1 : 0;
         t[i] = (int)cur;
     }
+}
+
+// SpeechT5ScaledPositionalEncoding table, computed the way HF builds it in fp32 (modeling_speecht5.py:405-411):
+// div_j = exp(fl(2j) * fl(-ln(1e4)/768)), pe[p, 2j] = sin(fl(p) * div_j), pe[p, 2j+1] = cos(fl(p) * div_j).
+int build_text_pe(loco_handle* h, int rows) {
+    const int H = kHidden;
+    std::vector<float> tab((size_t)rows * H);
+    const float neg = (float)(-(log(10000.0) / (double)H));
+    for (int j = 0; j < H / 2; ++j) {
+        const float div = (float)exp((double)((float)(2 * j) * neg));
+        for (int p = 0; p < rows; ++p) {
+            const float ang = (float)p * div;
+            tab[(size_t)p * H + 2 * j] = (float)sin((double)ang);
+            tab[(size_t)p * H + 2 * j + 1] = (float)cos((double)ang);
+        }
+    }
+    int rc = upload(h, tab, &h->txt_pe);
+    if (rc) return rc;
+    h->txt_pe_rows = rows;
+    return 0;
+}
+
+// Geometry of a text batch: a row is a token, utterances back to back (no slot padding), only the transformer buffers.
+int make_layout_text(loco_handle* h, const int32_t* n_tokens, int n_utts, Layout* L) {
+    L->n_utts = n_utts;
+    L->meta.resize(n_utts);
+    int64_t row = 0;
+    for (int u = 0; u < n_utts; ++u) {
+        if (n_tokens[u] <= 0) return fail(h, LOCO_ERR_INVALID, "text " + std::to_string(u) + " is empty");
+        UttMeta& m = L->meta[u];
+        m.sample_off = row;
+        m.n_samples = n_tokens[u];
+        m.t0 = n_tokens[u];
+        m.t6 = n_tokens[u];
+        m.row6 = (int32_t)row;
+        m.slot6 = n_tokens[u];
+        m.out_row = (int32_t)row;
+        row += n_tokens[u];
+        for (int f = 0; f < m.t6; f += 128) L->pc_tiles.push_back({m.row6 + f, f, m.t6, 0});
+        if (m.t6 > L->max_t6) L->max_t6 = m.t6;
+        if (m.slot6 > L->max_slot6) L->max_slot6 = m.slot6;
+    }
+    if (row > (int64_t)INT32_MAX / 4) return fail(h, LOCO_ERR_INVALID, "text batch too large");
+    L->R6 = row;
+    L->total_frames = row;
+    L->total_samples = row;
+    size_t p = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = p;
+        p = align_up(p + bytes);
+        return o;
+    };
+    L->off_meta = take((size_t)n_utts * sizeof(UttMeta));
+    L->off_at_tiles = take(L->pc_tiles.size() * sizeof(PcTile));
+    L->off_at_utts = take((size_t)n_utts * sizeof(int32_t));
+    L->off_rowframe = take((size_t)L->R6 * sizeof(int32_t));
+    auto add = [&](const char* name, int64_t rows, int64_t cols) {
+        Buf b;
+        b.rows = rows;
+        b.cols = cols;
+        b.off = take((size_t)rows * cols * sizeof(bf16));
+        L->bufs[name] = b;
+    };
+    add("x", L->R6, kHidden);
+    add("qkv", L->R6, 3 * kHidden);
+    add("ctx", L->R6, kHidden);
+    add("attn_res", L->R6, kHidden);
+    add("ln1", L->R6, kHidden);
+    add("mid", L->R6, kFfn);
+    add("ffn_res", L->R6, kHidden);
+    L->bufs["enc_in"] = L->bufs["x"];
+    L->bytes = p;
+    return 0;
 }
 
 int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L) {
@@ -459,7 +539,8 @@ int loco_load_tensor(loco_handle* h, const char* key, const void* data, const in
     if (!h || !key || !data || ndim < 0 || ndim > 4) return fail(h, LOCO_ERR_INVALID, "loco_load_tensor: bad argument");
     if (h->finalized) return fail(h, LOCO_ERR_STATE, "weights already finalized");
     const std::string k = canon_key(key);
-    if (k == "prenet.masked_spec_embed" || k.find("pos_sinusoidal_embed") != std::string::npos) return LOCO_OK;  // ignored
+    if (k == "prenet.masked_spec_embed" || k.find("pos_sinusoidal_embed") != std::string::npos || k == "prenet.encode_positions.pe")
+        return LOCO_OK;  // ignored: unused in eval / regenerated analytically
     const bool known = k.compare(0, 7, "prenet.") == 0 || k.compare(0, 16, "wrapped_encoder.") == 0;
     if (!known) return fail(h, LOCO_ERR_WEIGHTS, "unknown tensor key: " + std::string(key));
     HostTensor t;
@@ -489,6 +570,23 @@ int loco_finalize_weights(loco_handle* h) {
     CK(cudaSetDevice(h->device));
     int rc;
     const std::string fe = "prenet.feature_encoder.conv_layers.";
+    h->has_speech = h->host.count(fe + "0.conv.weight") != 0;
+    h->has_text = h->host.count("prenet.embed_tokens.weight") != 0;
+    if (!h->has_speech && !h->has_text)
+        return fail(h, LOCO_ERR_WEIGHTS, "no prenet weights: neither prenet.feature_encoder.* (speech) nor prenet.embed_tokens.weight (text)");
+    if (h->has_text) {
+        const HostTensor& e = h->host["prenet.embed_tokens.weight"];
+        if (e.shape.size() != 2 || e.shape[1] != kHidden || e.shape[0] < 1)
+            return fail(h, LOCO_ERR_WEIGHTS, "bad shape for prenet.embed_tokens.weight: want [vocab, 768]");
+        h->txt_vocab = (int)e.shape[0];
+        std::vector<float> v(e.data);
+        if ((rc = upload(h, v, &h->txt_embed))) return rc;
+        auto a = h->host.find("prenet.encode_positions.alpha");
+        if (a == h->host.end() || a->second.numel() != 1) return fail(h, LOCO_ERR_WEIGHTS, "missing tensor: prenet.encode_positions.alpha");
+        h->txt_alpha = a->second.data[0];
+        if ((rc = build_text_pe(h, 1024))) return rc;
+    }
+    if (h->has_speech) {
     if ((rc = upload_f32(h, fe + "0.conv.weight", {512, 1, 10}, &h->w0))) return rc;
     if ((rc = upload_f32(h, fe + "0.layer_norm.weight", {512}, &h->gn_w))) return rc;
     if ((rc = upload_f32(h, fe + "0.layer_norm.bias", {512}, &h->gn_b))) return rc;
@@ -531,6 +629,7 @@ int loco_finalize_weights(loco_handle* h) {
         if ((rc = upload(h, wt, &h->pos_w_tc))) return rc;
         if ((rc = upload_f32(h, "prenet.pos_conv_embed.conv.bias", {768}, &h->pos_b))) return rc;
     }
+    }  // has_speech
     if ((rc = upload_f32(h, "wrapped_encoder.layer_norm.weight", {768}, &h->eln_w))) return rc;
     if ((rc = upload_f32(h, "wrapped_encoder.layer_norm.bias", {768}, &h->eln_b))) return rc;
     if ((rc = upload_bf16(h, "wrapped_encoder.embed_positions.pe_k.weight", {320, 64}, &h->pe_k))) return rc;
@@ -575,61 +674,20 @@ int loco_finalize_weights(loco_handle* h) {
         if ((rc = upload_f32(h, p + "final_layer_norm.weight", {768}, &w.ln2_w))) return rc;
         if ((rc = upload_f32(h, p + "final_layer_norm.bias", {768}, &w.ln2_b))) return rc;
     }
-    if ((rc = build_sin_table(h, h->cfg.max_speech_positions + h->cfg.pad_token_id + 3))) return rc;
+    if (h->has_speech && (rc = build_sin_table(h, h->cfg.max_speech_positions + h->cfg.pad_token_id + 3))) return rc;
     h->host.clear();
     h->finalized = true;
     return LOCO_OK;
 }
 
-int loco_plan(loco_handle* h, const int32_t* n_samples, int n_utts, int32_t* frames, int32_t* rows, int64_t* total_frames,
-              size_t* workspace_bytes) {
-    if (!h || (!n_samples && n_utts > 0)) return fail(h, LOCO_ERR_INVALID, "loco_plan: bad argument");
-    Layout L;
-    int rc = make_layout(h, n_samples, n_utts, &L);
-    if (rc) return rc;
-    for (int u = 0; u < n_utts; ++u) {
-        if (frames) frames[u] = L.meta[u].t6;
-        if (rows) rows[u] = L.meta[u].row6;
-    }
-    if (total_frames) *total_frames = L.total_frames;
-    if (workspace_bytes) *workspace_bytes = L.bytes;
-    return LOCO_OK;
-}
-
-int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples, int n_utts, float* pooled_dev, float* hidden_dev,
-                void* workspace_dev, size_t workspace_bytes, void* stream) {
-    if (!h) return LOCO_ERR_INVALID;
-    if (!h->finalized) return fail(h, LOCO_ERR_STATE, "loco_encode before loco_finalize_weights");
-    if (n_utts == 0) return LOCO_OK;
-    if (!wave_dev || !n_samples || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode: null argument");
-    if ((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) != 0) return fail(h, LOCO_ERR_INVALID, "workspace must be 1024-byte aligned");
-    if ((reinterpret_cast<uintptr_t>(wave_dev) & 3) != 0) return fail(h, LOCO_ERR_INVALID, "wave_dev must be 4-byte aligned");
-    Layout& L = h->last;
-    L = Layout();
-    int rc = make_layout(h, n_samples, n_utts, &L);
-    if (rc) return rc;
-    if (workspace_bytes < L.bytes)
-        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes) + " bytes, got " + std::to_string(workspace_bytes));
-    CK(cudaSetDevice(h->device));
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (L.max_t6 + h->cfg.pad_token_id + 1 >= h->sin_rows) {  // HF grows its table on demand too (HF:331-333)
-        CK(cudaStreamSynchronize(s));
-        if ((rc = build_sin_table(h, L.max_t6 + h->cfg.pad_token_id + 1024))) return rc;
-    }
-    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
-    h->last_ws = workspace_dev;
+// The 12 post-LN transformer layers + final LayerNorm / masked mean-pool, shared by the speech and the text paths
+// (SpeechT5Encoder.forward, HF modeling_speecht5.py:1250-1338).  Expects B("x") = encoder input after its LayerNorm and
+// the per-utterance metadata already in the workspace.
+static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, float* pooled_dev, float* hidden_dev, cudaStream_t s) {
+    int rc;
     auto B = [&](const char* name) { return reinterpret_cast<bf16*>(ws + L.bufs[name].off); };
     UttMeta* meta = reinterpret_cast<UttMeta*>(ws + L.off_meta);
-    double* partial = reinterpret_cast<double*>(ws + L.off_partial);
-    float* scale = reinterpret_cast<float*>(ws + L.off_scale);
-    float* shift = reinterpret_cast<float*>(ws + L.off_shift);
-    int32_t* row_frame = reinterpret_cast<int32_t*>(ws + L.off_rowframe);
     const int R6 = (int)L.R6;
-
-    // pageable source: the runtime stages the bytes before returning, so `L.meta` may be reused at once
-    CK(cudaMemcpyAsync(meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta), cudaMemcpyHostToDevice, s));
-    PcTile* pc_tiles = reinterpret_cast<PcTile*>(ws + L.off_pctiles);
-    CK(cudaMemcpyAsync(pc_tiles, L.pc_tiles.data(), L.pc_tiles.size() * sizeof(PcTile), cudaMemcpyHostToDevice, s));
     // ---- attention work lists.  The kernel is chosen PER UTTERANCE by its own frame count, never by its batch-mates, so
     // an utterance's result does not depend on the batch it travels in.  Measured with tools/attn_sweep.py (ms per layer
     // at 64k frames, tcgen05 / mma.sync): 64 frames 0.33 / 0.20, 96: 0.26 / 0.28, 128: 0.25 / 0.31, 136: 0.50 / 0.41,
@@ -654,55 +712,12 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
     int32_t* at_utts_dev = reinterpret_cast<int32_t*>(ws + L.off_at_utts);
     if (!at_tiles.empty()) CK(cudaMemcpyAsync(at_tiles_dev, at_tiles.data(), at_tiles.size() * sizeof(PcTile), cudaMemcpyHostToDevice, s));
     if (!at_utts.empty()) CK(cudaMemcpyAsync(at_utts_dev, at_utts.data(), at_utts.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    for (int i = 0; i < 6; ++i) {  // the 8 pad frames the last implicit-GEMM rows of layer i+1 may touch
-        char nm[16];
-        snprintf(nm, sizeof nm, "conv%d", i);
-        const Buf& b = L.bufs[nm];
-        CK(cudaMemsetAsync(ws + b.off + (size_t)b.rows * kConvDim * 2, 0, (size_t)8 * kConvDim * 2, s));
-    }
-    LAUNCH(CAT_ROWOPS, launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
     // slot padding rows of ctx are never written by the attention kernels; keep them finite (zero) so they stay finite
     // through every later layer -- the tcgen05 attention multiplies masked (P = 0) key rows into O, and 0 * NaN = NaN
     CK(cudaMemsetAsync(ws + L.bufs["ctx"].off, 0, (size_t)L.R6 * kHidden * sizeof(bf16), s));
     alignas(64) CUtensorMap qkv_map;
     if (make_tensor_map_bf16_sw128(&qkv_map, B("qkv"), 3 * kHidden, (uint64_t)L.R6, 3 * kHidden, 32))
         return fail(h, LOCO_ERR_CUDA, "cuTensorMapEncodeTiled failed for qkv");
-
-    // ---- conv feature encoder -----------------------------------------------------------------------
-    LAUNCH(CAT_FRONTEND, launch_wave_stats(wave_dev, meta, n_utts, L.chunks, h->w0, h->gn_w, h->gn_b, partial, scale, shift, s), 2);
-    LAUNCH(CAT_FRONTEND, launch_conv0(wave_dev, meta, n_utts, L.max_slot6 << 6, h->w0, scale, shift, B("conv0"), s), 1);
-    for (int i = 1; i < 7; ++i) {
-        char in[16], out[16];
-        snprintf(in, sizeof in, "conv%d", i - 1);
-        snprintf(out, sizeof out, "conv%d", i);
-        const int K = h->cfg.conv_kernel[i] * kConvDim;
-        const int64_t rows_in = L.bufs[in].rows + 8;
-        GemmArgs g = {};
-        g.A = B(in);
-        g.lda = 2 * kConvDim;
-        g.a_rows_alloc = (rows_in * kConvDim - K) / (2 * kConvDim) + 1;
-        g.W = h->conv_w[i];
-        g.C = B(out);
-        g.ldc = kConvDim;
-        g.M = (int)L.bufs[out].rows;
-        g.N = kConvDim;
-        g.K = K;
-        g.epilogue = EPI_BIAS_GELU;
-        if ((rc = run_gemm(h, g, s))) return rc;
-    }
-    // ---- feature projection, positional conv, sinusoid, encoder input LayerNorm -------------------------
-    LAUNCH(CAT_ROWOPS, launch_layernorm(B("conv6"), B("proj_ln"), h->pln_w, h->pln_b, R6, kConvDim, s), 1);
-    {
-        GemmArgs g = {};
-        g.A = B("proj_ln"); g.lda = kConvDim; g.a_rows_alloc = R6; g.W = h->proj_w; g.C = B("proj"); g.ldc = kHidden;
-        g.bias = h->proj_b; g.M = R6; g.N = kHidden; g.K = kConvDim; g.epilogue = EPI_BIAS;
-        if ((rc = run_gemm(h, g, s))) return rc;
-    }
-    if (h->posconv_impl == 1)
-        LAUNCH(CAT_POSCONV, launch_posconv(B("proj"), h->pos_w, h->pos_b, meta, n_utts, L.max_t6, B("pos_conv"), s), 1);
-    else
-        LAUNCH(CAT_POSCONV, launch_posconv_tc(B("proj"), h->pos_w_tc, h->pos_b, pc_tiles, (int)L.pc_tiles.size(), B("pos_conv"), s), 1);
-    LAUNCH(CAT_ROWOPS, launch_prenet_ln(B("proj"), B("pos_conv"), h->sin_table, row_frame, B("x"), h->eln_w, h->eln_b, R6, s), 1);
 
     // ---- transformer layers (post-LN) -------------------------------------------------------------------
     const int n_layers = (int)h->layers.size();
@@ -739,6 +754,102 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         }
     }
     return LOCO_OK;
+}
+
+int loco_plan(loco_handle* h, const int32_t* n_samples, int n_utts, int32_t* frames, int32_t* rows, int64_t* total_frames,
+              size_t* workspace_bytes) {
+    if (!h || (!n_samples && n_utts > 0)) return fail(h, LOCO_ERR_INVALID, "loco_plan: bad argument");
+    Layout L;
+    int rc = make_layout(h, n_samples, n_utts, &L);
+    if (rc) return rc;
+    for (int u = 0; u < n_utts; ++u) {
+        if (frames) frames[u] = L.meta[u].t6;
+        if (rows) rows[u] = L.meta[u].row6;
+    }
+    if (total_frames) *total_frames = L.total_frames;
+    if (workspace_bytes) *workspace_bytes = L.bytes;
+    return LOCO_OK;
+}
+
+int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples, int n_utts, float* pooled_dev, float* hidden_dev,
+                void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h) return LOCO_ERR_INVALID;
+    if (!h->finalized) return fail(h, LOCO_ERR_STATE, "loco_encode before loco_finalize_weights");
+    if (!h->has_speech) return fail(h, LOCO_ERR_STATE, "loco_encode: this handle was loaded without the speech prenet (text-only weights)");
+    if (n_utts == 0) return LOCO_OK;
+    if (!wave_dev || !n_samples || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode: null argument");
+    if ((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) != 0) return fail(h, LOCO_ERR_INVALID, "workspace must be 1024-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(wave_dev) & 3) != 0) return fail(h, LOCO_ERR_INVALID, "wave_dev must be 4-byte aligned");
+    Layout& L = h->last;
+    L = Layout();
+    int rc = make_layout(h, n_samples, n_utts, &L);
+    if (rc) return rc;
+    if (workspace_bytes < L.bytes)
+        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes) + " bytes, got " + std::to_string(workspace_bytes));
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (L.max_t6 + h->cfg.pad_token_id + 1 >= h->sin_rows) {  // HF grows its table on demand too (HF:331-333)
+        CK(cudaStreamSynchronize(s));
+        if ((rc = build_sin_table(h, L.max_t6 + h->cfg.pad_token_id + 1024))) return rc;
+    }
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
+    h->last_ws = workspace_dev;
+    auto B = [&](const char* name) { return reinterpret_cast<bf16*>(ws + L.bufs[name].off); };
+    UttMeta* meta = reinterpret_cast<UttMeta*>(ws + L.off_meta);
+    double* partial = reinterpret_cast<double*>(ws + L.off_partial);
+    float* scale = reinterpret_cast<float*>(ws + L.off_scale);
+    float* shift = reinterpret_cast<float*>(ws + L.off_shift);
+    int32_t* row_frame = reinterpret_cast<int32_t*>(ws + L.off_rowframe);
+    const int R6 = (int)L.R6;
+
+    // pageable source: the runtime stages the bytes before returning, so `L.meta` may be reused at once
+    CK(cudaMemcpyAsync(meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta), cudaMemcpyHostToDevice, s));
+    PcTile* pc_tiles = reinterpret_cast<PcTile*>(ws + L.off_pctiles);
+    CK(cudaMemcpyAsync(pc_tiles, L.pc_tiles.data(), L.pc_tiles.size() * sizeof(PcTile), cudaMemcpyHostToDevice, s));
+    for (int i = 0; i < 6; ++i) {  // the 8 pad frames the last implicit-GEMM rows of layer i+1 may touch
+        char nm[16];
+        snprintf(nm, sizeof nm, "conv%d", i);
+        const Buf& b = L.bufs[nm];
+        CK(cudaMemsetAsync(ws + b.off + (size_t)b.rows * kConvDim * 2, 0, (size_t)8 * kConvDim * 2, s));
+    }
+    LAUNCH(CAT_ROWOPS, launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
+    // ---- conv feature encoder -----------------------------------------------------------------------
+    LAUNCH(CAT_FRONTEND, launch_wave_stats(wave_dev, meta, n_utts, L.chunks, h->w0, h->gn_w, h->gn_b, partial, scale, shift, s), 2);
+    LAUNCH(CAT_FRONTEND, launch_conv0(wave_dev, meta, n_utts, L.max_slot6 << 6, h->w0, scale, shift, B("conv0"), s), 1);
+    for (int i = 1; i < 7; ++i) {
+        char in[16], out[16];
+        snprintf(in, sizeof in, "conv%d", i - 1);
+        snprintf(out, sizeof out, "conv%d", i);
+        const int K = h->cfg.conv_kernel[i] * kConvDim;
+        const int64_t rows_in = L.bufs[in].rows + 8;
+        GemmArgs g = {};
+        g.A = B(in);
+        g.lda = 2 * kConvDim;
+        g.a_rows_alloc = (rows_in * kConvDim - K) / (2 * kConvDim) + 1;
+        g.W = h->conv_w[i];
+        g.C = B(out);
+        g.ldc = kConvDim;
+        g.M = (int)L.bufs[out].rows;
+        g.N = kConvDim;
+        g.K = K;
+        g.epilogue = EPI_BIAS_GELU;
+        if ((rc = run_gemm(h, g, s))) return rc;
+    }
+    // ---- feature projection, positional conv, sinusoid, encoder input LayerNorm -------------------------
+    LAUNCH(CAT_ROWOPS, launch_layernorm(B("conv6"), B("proj_ln"), h->pln_w, h->pln_b, R6, kConvDim, s), 1);
+    {
+        GemmArgs g = {};
+        g.A = B("proj_ln"); g.lda = kConvDim; g.a_rows_alloc = R6; g.W = h->proj_w; g.C = B("proj"); g.ldc = kHidden;
+        g.bias = h->proj_b; g.M = R6; g.N = kHidden; g.K = kConvDim; g.epilogue = EPI_BIAS;
+        if ((rc = run_gemm(h, g, s))) return rc;
+    }
+    if (h->posconv_impl == 1)
+        LAUNCH(CAT_POSCONV, launch_posconv(B("proj"), h->pos_w, h->pos_b, meta, n_utts, L.max_t6, B("pos_conv"), s), 1);
+    else
+        LAUNCH(CAT_POSCONV, launch_posconv_tc(B("proj"), h->pos_w_tc, h->pos_b, pc_tiles, (int)L.pc_tiles.size(), B("pos_conv"), s), 1);
+    LAUNCH(CAT_ROWOPS, launch_prenet_ln(B("proj"), B("pos_conv"), h->sin_table, row_frame, B("x"), h->eln_w, h->eln_b, R6, s), 1);
+
+    return run_transformer(h, L, ws, n_utts, pooled_dev, hidden_dev, s);
 }
 
 int loco_host_workspace_bytes(loco_handle* h, const int32_t* n_samples, int n_utts, int want_hidden, size_t* bytes) {
@@ -778,6 +889,49 @@ int loco_encode_host(loco_handle* h, const float* wave_host, const int32_t* n_sa
     if (hidden_host) CK(cudaMemcpyAsync(hidden_host, hidden_dev, hidden_bytes, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return LOCO_OK;
+}
+
+int loco_plan_text(loco_handle* h, const int32_t* n_tokens, int n_utts, int32_t* rows, int64_t* total_tokens, size_t* workspace_bytes) {
+    if (!h || (!n_tokens && n_utts > 0)) return fail(h, LOCO_ERR_INVALID, "loco_plan_text: bad argument");
+    Layout L;
+    int rc = make_layout_text(h, n_tokens, n_utts, &L);
+    if (rc) return rc;
+    for (int u = 0; u < n_utts; ++u)
+        if (rows) rows[u] = L.meta[u].row6;
+    if (total_tokens) *total_tokens = L.total_frames;
+    if (workspace_bytes) *workspace_bytes = L.bytes;
+    return LOCO_OK;
+}
+
+int loco_encode_text(loco_handle* h, const int32_t* tokens_dev, const int32_t* n_tokens, int n_utts, float* pooled_dev, float* hidden_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h) return LOCO_ERR_INVALID;
+    if (!h->finalized) return fail(h, LOCO_ERR_STATE, "loco_encode_text before loco_finalize_weights");
+    if (!h->has_text) return fail(h, LOCO_ERR_STATE, "loco_encode_text: this handle was loaded without the text prenet (prenet.embed_tokens.weight)");
+    if (n_utts == 0) return LOCO_OK;
+    if (!tokens_dev || !n_tokens || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode_text: null argument");
+    if ((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) != 0) return fail(h, LOCO_ERR_INVALID, "workspace must be 1024-byte aligned");
+    Layout& L = h->last;
+    L = Layout();
+    int rc = make_layout_text(h, n_tokens, n_utts, &L);
+    if (rc) return rc;
+    if (workspace_bytes < L.bytes)
+        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes) + " bytes, got " + std::to_string(workspace_bytes));
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (L.max_t6 > h->txt_pe_rows) {      // HF's table stops at max_text_positions (450); this one grows on demand
+        CK(cudaStreamSynchronize(s));
+        if ((rc = build_text_pe(h, L.max_t6 + 1024))) return rc;
+    }
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
+    h->last_ws = workspace_dev;
+    UttMeta* meta = reinterpret_cast<UttMeta*>(ws + L.off_meta);
+    int32_t* row_frame = reinterpret_cast<int32_t*>(ws + L.off_rowframe);
+    CK(cudaMemcpyAsync(meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta), cudaMemcpyHostToDevice, s));
+    LAUNCH(CAT_ROWOPS, launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
+    LAUNCH(CAT_ROWOPS, launch_text_prenet_ln(tokens_dev, h->txt_embed, h->txt_pe, h->txt_alpha, h->txt_vocab, row_frame,
+                                             reinterpret_cast<bf16*>(ws + L.bufs["x"].off), h->eln_w, h->eln_b, (int)L.R6, s), 1);
+    return run_transformer(h, L, ws, n_utts, pooled_dev, hidden_dev, s);
 }
 
 int64_t loco_launch_count(const loco_handle* h) { return h ? h->launches : 0; }

@@ -72,6 +72,9 @@ int launch_final_ln_pool(const bf16* x, const float* gamma, const float* beta, c
                          float* pooled /*[n,768]*/, float* hidden_out_or_null, cudaStream_t s);
 // row_frame[r] = frame index of row r inside its utterance, or -1 for slot padding rows.
 int launch_row_frames(const UttMeta* meta, int n_utts, int max_slot6, int32_t* row_frame, cudaStream_t s);
+// text modality: y[row] = LayerNorm(embed[tokens[row]] + alpha * pe[row_frame[row]])
+int launch_text_prenet_ln(const int32_t* tokens, const float* embed /*[vocab, 768]*/, const float* pe /*[positions, 768]*/, float alpha,
+                          int vocab, const int32_t* row_frame, bf16* y, const float* gamma, const float* beta, int rows, cudaStream_t s);
 
 // ---- positional conv on tcgen05 (posconv_tc.cu) ------------------------------------------------
 struct PcTile {      // one 128-frame output tile of one utterance

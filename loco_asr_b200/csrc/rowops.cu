@@ -133,6 +133,36 @@ __global__ void __launch_bounds__(256) prenet_ln_kernel(const bf16* __restrict__
     r.store(y + (int64_t)row * kHidden, lane);
 }
 
+// Text prenet + encoder input LayerNorm (SpeechT5TextEncoderPrenet, HF modeling_speecht5.py:765-779: embed_tokens then
+// SpeechT5ScaledPositionalEncoding, HF:400-422: emb + alpha * pe[position]; SpeechT5Encoder.layer_norm, HF:1292).
+// In the text layout a row IS a token (no slot padding), so tokens[row] is the row's id and row_frame[row] its position.
+__global__ void __launch_bounds__(256) text_prenet_ln_kernel(const int32_t* __restrict__ tokens, const float* __restrict__ embed,
+                                                              const float* __restrict__ pe, float alpha, int vocab,
+                                                              const int32_t* __restrict__ row_frame, bf16* __restrict__ y,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta, int rows) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int pos = row_frame[row];
+    RowVec<kHidden> r;
+#pragma unroll
+    for (int i = 0; i < RowVec<kHidden>::kChunks * 8; ++i) r.v[i] = 0.f;
+    if (pos < 0) {
+        r.store(y + (int64_t)row * kHidden, lane);
+        return;
+    }
+    const int tok = min(max(tokens[row], 0), vocab - 1);      // ids are validated on the host side of the ABI
+    r.add_f32(embed + (int64_t)tok * kHidden, lane);
+    RowVec<kHidden> p;
+#pragma unroll
+    for (int i = 0; i < RowVec<kHidden>::kChunks * 8; ++i) p.v[i] = 0.f;
+    p.add_f32(pe + (int64_t)pos * kHidden, lane);
+#pragma unroll
+    for (int i = 0; i < RowVec<kHidden>::kChunks * 8; ++i) r.v[i] = fmaf(alpha, p.v[i], r.v[i]);
+    r.normalize(gamma, beta, lane);
+    r.store(y + (int64_t)row * kHidden, lane);
+}
+
 // One block per utterance: LayerNorm every valid frame, accumulate column sums per warp in registers,
 // reduce across the 8 warps in a fixed order (deterministic), write mean over the utterance's T frames.
 __global__ void __launch_bounds__(256) final_ln_pool_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
@@ -189,6 +219,13 @@ int launch_prenet_ln(const bf16* h, const bf16* pc, const float* sin_table, cons
                      const float* gamma, const float* beta, int rows, cudaStream_t s) {
     if (rows <= 0) return 0;
     prenet_ln_kernel<<<(rows + 7) / 8, 256, 0, s>>>(h, pc, sin_table, row_frame, y, gamma, beta, rows);
+    return (int)cudaGetLastError();
+}
+
+int launch_text_prenet_ln(const int32_t* tokens, const float* embed, const float* pe, float alpha, int vocab, const int32_t* row_frame,
+                          bf16* y, const float* gamma, const float* beta, int rows, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    text_prenet_ln_kernel<<<(rows + 7) / 8, 256, 0, s>>>(tokens, embed, pe, alpha, vocab, row_frame, y, gamma, beta, rows);
     return (int)cudaGetLastError();
 }
 

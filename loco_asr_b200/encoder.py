@@ -83,6 +83,7 @@ class LocoSpeechT5Encoder:
         _lib.check(self._lib, None, rc, "loco_create")
         self._h = h
         self._finalized = False
+        self._text_vocab = 0
         self._workspace: Optional[torch.Tensor] = None
         self.prenet = _SubmoduleShim(self, "prenet.")
         self.wrapped_encoder = _SubmoduleShim(self, "wrapped_encoder.")
@@ -120,6 +121,8 @@ class LocoSpeechT5Encoder:
         if self._finalized:
             raise _lib.LocoError("weights are already finalized; create a new encoder to load another checkpoint")
         for k, v in sd.items():
+            if k.endswith("prenet.embed_tokens.weight"):
+                self._text_vocab = int(v.shape[0])
             if not (k.startswith("prenet.") or k.startswith("wrapped_encoder.") or k.startswith("speecht5.encoder.")
                     or k.startswith("encoder.")):
                 continue  # decoder / head tensors of a full-model checkpoint are not on this path
@@ -213,6 +216,67 @@ class LocoSpeechT5Encoder:
         _lib.check(self._lib, self._h, rc, "loco_encode_host")
         return pooled_host
 
+    # ------------------------------------------------------------------ text modality (reference :79-93)
+    def encode_text_packed(self, tokens: torch.Tensor, n_tokens: Sequence[int], return_hidden: bool = False):
+        """tokens: int32[sum(n_tokens)] on this device, texts concatenated without padding.  Each text is encoded alone.
+        Returns pooled f32[B, 768] (and the compact last_hidden_state f32[sum n_tokens, 768] if asked)."""
+        self.finalize()
+        if tokens.device != self.device or tokens.dtype != torch.int32 or not tokens.is_contiguous():
+            raise _lib.LocoError("encode_text_packed wants a contiguous int32 token tensor on " + str(self.device))
+        nt = np.ascontiguousarray(np.asarray(n_tokens, dtype=np.int32))
+        n = int(nt.shape[0])
+        if int(nt.sum()) != tokens.numel():
+            raise _lib.LocoError(f"sum(n_tokens)={int(nt.sum())} does not match the token count {tokens.numel()}")
+        total, wsb = C.c_int64(), C.c_size_t()
+        rows = np.zeros(n, dtype=np.int32)
+        rc = self._lib.loco_plan_text(self._h, nt.ctypes.data, n, rows.ctypes.data, C.byref(total), C.byref(wsb))
+        _lib.check(self._lib, self._h, rc, "loco_plan_text")
+        ws = self._get_workspace(int(wsb.value))
+        pooled = torch.empty(n, self.config.hidden_size, dtype=torch.float32, device=self.device)
+        hidden = torch.empty(int(total.value), self.config.hidden_size, dtype=torch.float32, device=self.device) if return_hidden else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = self._lib.loco_encode_text(self._h, tokens.data_ptr(), nt.ctypes.data, n, pooled.data_ptr(),
+                                            hidden.data_ptr() if hidden is not None else None, ws.data_ptr(), ws.numel(),
+                                            C.c_void_p(stream))
+        _lib.check(self._lib, self._h, rc, "loco_encode_text")
+        info = {"frames": nt.copy(), "rows": rows, "total_frames": int(total.value), "workspace_bytes": int(wsb.value)}
+        self._last_plan = info
+        if return_hidden:
+            return pooled, hidden, info
+        return pooled
+
+    def _call_text(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], return_last_hidden_state: bool):
+        """``encoder(texts.input_ids)`` of the reference's text branch (:88): int[B, L_max].  The reference passes no mask,
+        so padded positions are real tokens to it; the same happens here.  With a mask each text keeps its own tokens."""
+        ids = input_ids.to(self.device)
+        if ids.dim() == 1:
+            ids = ids[None]
+        B, Lmax = ids.shape
+        if attention_mask is None:
+            lengths = np.full(B, Lmax, dtype=np.int32)
+            tok = ids.reshape(-1)
+        else:
+            am = attention_mask.to(self.device)
+            lengths = am.sum(dim=-1).to(torch.int32).cpu().numpy()
+            keep = torch.arange(Lmax, device=self.device)[None, :] < torch.as_tensor(lengths, device=self.device)[:, None]
+            tok = ids[keep]
+        if tok.numel() and (int(tok.min()) < 0 or int(tok.max()) >= self.text_vocab_size()):
+            raise IndexError("token id out of range for the text prenet's embedding table")      # what nn.Embedding raises
+        tok = tok.to(torch.int32).contiguous()
+        if not return_last_hidden_state:
+            return LocoEncoderOutput(None, self.encode_text_packed(tok, lengths), torch.as_tensor(lengths, dtype=torch.int64))
+        pooled, hidden, info = self.encode_text_packed(tok, lengths, return_hidden=True)
+        frames = torch.as_tensor(lengths, dtype=torch.int64)
+        tmax = int(frames.max())
+        out = torch.zeros(B, tmax, self.config.hidden_size, dtype=torch.float32, device=self.device)
+        keep_f = torch.arange(tmax, device=self.device)[None, :] < frames.to(self.device)[:, None]
+        out[keep_f] = hidden
+        return LocoEncoderOutput(out, pooled, frames)
+
+    def text_vocab_size(self) -> int:
+        return int(self._text_vocab)
+
     # ------------------------------------------------------------------ the reference's call: encoder(**audios)
     def __call__(self, input_values: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                  output_attentions=None, output_hidden_states=None, return_dict=None, return_last_hidden_state: bool = True,
@@ -221,6 +285,8 @@ class LocoSpeechT5Encoder:
         produced by ``SpeechT5Processor(audio=..., padding="longest")`` (reference :60)."""
         if output_attentions or output_hidden_states:
             raise _lib.LocoError("attention maps / per-layer hidden states are never materialised by the fused kernels")
+        if not torch.is_floating_point(input_values):      # token ids: the text branch of the reference scripts
+            return self._call_text(input_values, attention_mask, return_last_hidden_state)
         if input_values.dim() == 1:
             input_values = input_values[None]
         iv = input_values.to(self.device, dtype=torch.float32)

@@ -1,6 +1,6 @@
-"""Drop-in for ``speech_text/extract_speecht5_{base,finetuned}_embeddings_slurp.py`` (audio modality).
+"""Drop-in for ``speech_text/extract_speecht5_{base,finetuned}_embeddings_slurp.py`` (audio and text modalities).
 
-Same CLI (``-m audio -s {train,devel,test,train_synthetic}``), same output files
+Same CLI (``-m {audio,text} -s {train,devel,test,train_synthetic}``), same output files
 (``extracted/{speecht5|speecht5_base}/<split>/<modality>/<slurp_id>_embedding_and_target.pickle`` holding
 ``{"id", "embedding": np.float32[T, 768], "target": one-hot[101]}``, reference :70-77,:111-113) that
 ``slurp_embeddings_and_targets.py:19-28`` and ``train_classifier.py`` read back -- but the loop is restructured
@@ -13,7 +13,10 @@ writes the reference's [T, 768].
 
 Run from the reference's ``speech_text/`` directory (so ``slurp_data`` / ``intent_classes`` import), or pass
 ``--classes-file`` and ``--synthetic N`` to exercise the pipeline without the SLURP corpus (not available offline).
-The ``-m text`` branch of the reference (text prenet) is not on the hot path and is not implemented.
+``-m text`` (reference :79-93) runs the sentences through the text prenet + the same encoder (``loco_encode_text``); it needs
+the SpeechT5 tokenizer (``--tokenizer``: a local ``SpeechT5Processor`` / ``SpeechT5Tokenizer`` directory, default the hub name
+the reference uses) and ``text_prenet_state_dict.pickle`` in the mapping folder.  Each sentence is encoded alone and
+unpadded; the reference's ``padding="longest"`` batches pass no attention mask, so its padded rows see the pad tokens.
 """
 from __future__ import annotations
 
@@ -56,8 +59,8 @@ def load_classes(path: Optional[str]) -> List[str]:
 
 
 # ------------------------------------------------------------------------------------------------ data
-def read_slurp_index(data_path: str, split: str):
-    """(slurp_id, audio_path, intent) per utterance; mirrors SLURPDataset.prepare_data (slurp_data.py:19-53),
+def read_slurp_index(data_path: str, split: str, modality: str = "audio"):
+    """(slurp_id, audio_path | sentence, intent) per utterance; mirrors SLURPDataset.prepare_data (slurp_data.py:19-53),
     including its recording choice (always ``recordings[0]`` -- the "headset" test there inspects dict keys)."""
     text_file = os.path.join(data_path, "dataset", "slurp", split + ".jsonl")
     audio_dir = os.path.join(data_path, "audio", "slurp_synth" if split == "train_synthetic" else "slurp_real")
@@ -67,7 +70,8 @@ def read_slurp_index(data_path: str, split: str):
             line = line.strip()
             if line:
                 it = json.loads(line)
-                items.append((it["slurp_id"], os.path.join(audio_dir, it["recordings"][0]["file"]), it["intent"]))
+                key = it["sentence"] if modality == "text" else os.path.join(audio_dir, it["recordings"][0]["file"])
+                items.append((it["slurp_id"], key, it["intent"]))
     return items
 
 
@@ -155,6 +159,63 @@ def run(encoder, items, waves_fn, binarize, folder: str, full_sequence: bool = F
     return len(todo)
 
 
+def load_tokenizer(name_or_path: str):
+    """sentence -> int64 token ids, as ``processor(text=...)`` gives the reference (:59): SpeechT5Tokenizer, character-level
+    sentencepiece, vocabulary 81, ``</s>`` appended."""
+    try:
+        from transformers import SpeechT5Tokenizer
+        tok = SpeechT5Tokenizer.from_pretrained(name_or_path)
+    except Exception as e:  # no network / no cache in this environment
+        raise SystemExit(f"cannot load the SpeechT5 tokenizer from {name_or_path!r} ({type(e).__name__}: {e}); "
+                         "pass --tokenizer <local directory> or use --synthetic") from e
+    return lambda sentence: np.asarray(tok(sentence)["input_ids"], dtype=np.int64)
+
+
+def run_text(encoder, items, tokens_fn, binarize, folder: str, full_sequence: bool = False, max_tokens: int = 65536,
+             writers: int = 8, resume: bool = True, log=print):
+    """Text modality: items [(slurp_id, sentence-key, intent)]; tokens_fn(key) -> int token ids.  Same files as run()."""
+    import torch
+    from .buckets import make_batches
+
+    os.makedirs(folder, exist_ok=True)
+    todo = [it for it in items if not (resume and os.path.exists(output_path(folder, it[0])))]
+    if len(todo) < len(items):
+        log(f"resume: {len(items) - len(todo)} of {len(items)} outputs already exist")
+    if not todo:
+        return 0
+    toks = [np.asarray(tokens_fn(it[1]), dtype=np.int64) for it in todo]
+    lengths = [len(t) for t in toks]
+    targets = binarize([it[2] for it in todo])
+    pool = ThreadPoolExecutor(max_workers=writers)
+    futures = []
+    order = sorted(range(len(todo)), key=lambda i: lengths[i])
+    start = 0
+    while start < len(order):
+        end, total = start, 0
+        while end < len(order) and (end == start or total + lengths[order[end]] <= max_tokens):
+            total += lengths[order[end]]
+            end += 1
+        idx = order[start:end]
+        start = end
+        packed = torch.from_numpy(np.concatenate([toks[i] for i in idx])).to(torch.int32).to(encoder.device)
+        nt = [lengths[i] for i in idx]
+        if full_sequence:
+            pooled, hidden, _ = encoder.encode_text_packed(packed, nt, return_hidden=True)
+            hidden = hidden.cpu().numpy()
+            off = 0
+            for j, i in enumerate(idx):
+                futures.append(pool.submit(write_item, folder, todo[i][0], hidden[off:off + nt[j]].copy(), targets[i]))
+                off += nt[j]
+        else:
+            pooled = encoder.encode_text_packed(packed, nt).cpu().numpy()
+            for j, i in enumerate(idx):
+                futures.append(pool.submit(write_item, folder, todo[i][0], pooled[j:j + 1].copy(), targets[i]))
+    for f in futures:
+        f.result()
+    pool.shutdown()
+    return len(todo)
+
+
 def main(argv=None):
     p = argparse.ArgumentParser(description="Extract SpeechT5 encoder embeddings from SLURP (B200 CUDA path)")
     p.add_argument("--modality", "-m", choices=["text", "audio"], required=True)
@@ -171,15 +232,24 @@ def main(argv=None):
     p.add_argument("--synthetic", type=int, default=0, help="use N synthetic SLURP-shaped utterances and random-init weights")
     p.add_argument("--device", default="cuda:0")
     p.add_argument("--max-frames", type=int, default=65536)
+    p.add_argument("--tokenizer", default="microsoft/speecht5_asr", help="text modality: SpeechT5 tokenizer name or local directory")
     a = p.parse_args(argv)
-    if a.modality != "audio":
-        raise SystemExit("only the audio modality (the speech-encoder hot path) is implemented")
     print(f"Extracting {a.modality} embeddings from SLURP {a.split} set using SpeechT5 (loco_asr_b200)")
 
     import torch
     from .encoder import LocoSpeechT5Encoder
     enc = LocoSpeechT5Encoder(device=a.device)
-    if a.synthetic:
+    text = a.modality == "text"
+    if a.synthetic and text:
+        from .synth import synth_state_dict, synth_text_prenet_state_dict
+        enc.load_state_dict({k: v for k, v in synth_state_dict(seed=1).items() if k.startswith("wrapped_encoder.")})
+        enc.load_state_dict(synth_text_prenet_state_dict(seed=1))
+        classes = load_classes(a.classes_file) if (a.classes_file or "intent_classes" in sys.modules) else [f"intent_{i:03d}" for i in range(101)]
+        rng = np.random.default_rng(1234)
+        sents = [np.concatenate([rng.integers(4, 81, size=int(rng.integers(8, 90))), [2]]) for _ in range(a.synthetic)]
+        items = [(f"synth{i}", i, classes[i % len(classes)]) for i in range(a.synthetic)]
+        waves_fn = lambda i: sents[i]
+    elif a.synthetic:
         from .synth import slurp_shaped_lengths, synth_state_dict, synth_wave
         enc.load_state_dict(synth_state_dict(seed=1))
         classes = load_classes(a.classes_file) if (a.classes_file or "intent_classes" in sys.modules) else [f"intent_{i:03d}" for i in range(101)]
@@ -194,14 +264,18 @@ def main(argv=None):
         else:
             with open(os.path.join(a.mapping_dir, "encoder_state_dict.pickle"), "rb") as fh:
                 enc.wrapped_encoder.load_state_dict(pickle.load(fh))
-            with open(os.path.join(a.mapping_dir, "speech_prenet_state_dict.pickle"), "rb") as fh:
+            prenet_file = "text_prenet_state_dict.pickle" if text else "speech_prenet_state_dict.pickle"   # reference :44-49
+            with open(os.path.join(a.mapping_dir, prenet_file), "rb") as fh:
                 enc.prenet.load_state_dict(pickle.load(fh))
-        items = read_slurp_index(a.data_path, a.split)
-        waves_fn = load_audio
+        items = read_slurp_index(a.data_path, a.split, a.modality)
+        waves_fn = load_tokenizer(a.tokenizer) if text else load_audio
     enc.finalize()
     print(f"{a.split} set size: {len(items)}")
-    n = run(enc, items, waves_fn, make_label_binarizer(classes), output_folder(a.out_root, a.version, a.split, a.modality),
-            full_sequence=a.full_sequence, max_frames=a.max_frames)
+    folder = output_folder(a.out_root, a.version, a.split, a.modality)
+    if text:
+        n = run_text(enc, items, waves_fn, make_label_binarizer(classes), folder, full_sequence=a.full_sequence, max_tokens=a.max_frames)
+    else:
+        n = run(enc, items, waves_fn, make_label_binarizer(classes), folder, full_sequence=a.full_sequence, max_frames=a.max_frames)
     print(f"wrote {n} files\nDone!")
 
 

@@ -147,3 +147,14 @@ def synth_head(seed: int = 3, n_classes: int = 101, hidden: int = 768):
     w = (torch.rand(n_classes, hidden, generator=g) * 2 - 1) * bound
     b = (torch.rand(n_classes, generator=g) * 2 - 1) * bound
     return w, b
+
+
+def synth_text_prenet_state_dict(vocab_size: int = 81, hidden_size: int = 768, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Random-init text prenet under the HF ``SpeechT5TextEncoderPrenet`` key names with the ``prenet.`` prefix
+    (``embed_tokens.weight``, ``encode_positions.alpha``; the padding row of the embedding is zero like nn.Embedding's)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed) + 7919)
+    emb = torch.randn(vocab_size, hidden_size, generator=g, dtype=torch.float32)
+    emb[1] = 0.0                                   # padding_idx = pad_token_id = 1
+    return {"prenet.embed_tokens.weight": emb,
+            "prenet.encode_positions.alpha": torch.tensor(1.0 + 0.25 * float(torch.randn((), generator=g)))}

@@ -33,6 +33,28 @@ def build_hf_encoder(state_dict: Dict[str, torch.Tensor] | None = None):
     return model
 
 
+def build_hf_text_encoder(state_dict: Dict[str, torch.Tensor]):
+    """The reference's text branch: SpeechT5ForTextToSpeech(...).speecht5.encoder == SpeechT5EncoderWithTextPrenet
+    (extract_speecht5_base_embeddings_slurp.py:79-88; HF modeling_speecht5.py:1377-1415)."""
+    from transformers import SpeechT5Config
+    from transformers.models.speecht5.modeling_speecht5 import SpeechT5EncoderWithTextPrenet
+
+    model = SpeechT5EncoderWithTextPrenet(SpeechT5Config()).eval()
+    sd = {k: v for k, v in state_dict.items() if k.startswith("wrapped_encoder.") or
+          k in ("prenet.embed_tokens.weight", "prenet.encode_positions.alpha")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    bad = [k for k in missing if "encode_positions.pe" not in k]
+    if bad or unexpected:
+        raise RuntimeError(f"state dict mismatch: missing={bad} unexpected={unexpected}")
+    return model
+
+
+@torch.no_grad()
+def hf_encode_text_unpadded(model, token_lists) -> List[torch.Tensor]:
+    """One text at a time, no padding (the reference passes no attention mask, so only unpadded calls are well defined)."""
+    return [model(torch.as_tensor(t, dtype=torch.long)[None]).last_hidden_state[0] for t in token_lists]
+
+
 @torch.no_grad()
 def hf_encode_unpadded(model, waves: Sequence[np.ndarray]) -> List[torch.Tensor]:
     """One utterance at a time, no padding: the per-utterance ground truth."""

@@ -6,6 +6,8 @@ Fixtures
   config1_hf.npz   BASELINE.json configs[0]: 16 utterances of 2.5-3.5 s, weights seed 0, waveform seed 0.
                    pooled f32[16,768] (mean over own frames), n_frames, first/last frame of each utterance,
                    and the reference's literal batch_size=2 padded run (informational).
+  text_hf.npz      text modality: 6 seeded token sequences (1..120 tokens) through the unmodified HF
+                   SpeechT5EncoderWithTextPrenet, weights seed 0 + text prenet seed 0: pooled, first / last token rows.
   short_taps.npz   one 0.4 s noise utterance (T=19, all taps) and one 1.3 s utterance (T=64, three taps): stage-by-stage taps of the oracle
                    restatement *after* it has been checked against the HF module to 2e-5.
 """
@@ -20,12 +22,40 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from loco_asr_b200.synth import synth_state_dict, synth_wave, config1_lengths  # noqa: E402
+from loco_asr_b200.synth import synth_state_dict, synth_text_prenet_state_dict, synth_wave, config1_lengths  # noqa: E402
 from oracle import speecht5_oracle as O  # noqa: E402
-from oracle.hf_reference import build_hf_encoder, hf_encode_unpadded, hf_encode_padded_batches  # noqa: E402
+from oracle.hf_reference import (build_hf_encoder, build_hf_text_encoder, hf_encode_padded_batches,  # noqa: E402
+                                 hf_encode_text_unpadded, hf_encode_unpadded)
 
 TAP_KEYS = ["conv0", "conv1", "conv6", "proj_ln", "proj", "pos_conv", "prenet_out", "enc_in", "l0_qkv", "l0_ctx",
             "l0_ln1", "l0_mid", "layer0", "layer5", "layer11"]
+
+
+TEXT_LENGTHS = [1, 7, 23, 64, 65, 120]
+
+
+def text_tokens(seed: int = 0, vocab: int = 81):
+    """Seeded token sequences: ids 4..vocab-1 with the </s> id 2 at the end (SpeechT5 tokenizer convention)."""
+    rng = np.random.default_rng(1000 + seed)
+    return [np.concatenate([rng.integers(4, vocab, size=n - 1), [2]]).astype(np.int64) for n in TEXT_LENGTHS]
+
+
+def text_state_dict(seed: int = 0):
+    sd = {k: v for k, v in synth_state_dict(seed=seed).items() if k.startswith("wrapped_encoder.")}
+    sd.update(synth_text_prenet_state_dict(seed=seed))
+    return sd
+
+
+def make_text(out_dir):
+    sd = text_state_dict(0)
+    model = build_hf_text_encoder(sd)
+    toks = text_tokens(0)
+    hs = hf_encode_text_unpadded(model, toks)
+    np.savez(os.path.join(out_dir, "text_hf.npz"),
+             lengths=np.asarray(TEXT_LENGTHS, dtype=np.int64), tokens=np.concatenate(toks),
+             pooled=torch.stack([h.mean(0) for h in hs]).numpy().astype(np.float32),
+             first_row=torch.stack([h[0] for h in hs]).numpy().astype(np.float32),
+             last_row=torch.stack([h[-1] for h in hs]).numpy().astype(np.float32), weights_seed=0)
 
 
 def main():
@@ -35,6 +65,9 @@ def main():
     model = build_hf_encoder(sd)
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    make_text(out_dir)
+    if "--text-only" in sys.argv:
+        return
 
     lengths = config1_lengths()
     waves = [synth_wave(n, 0, i) for i, n in enumerate(lengths)]

@@ -134,6 +134,12 @@ def encode_utterance(sd: Dict[str, torch.Tensor], wave: torch.Tensor, n_layers: 
     h = h + sinusoid_rows(torch.arange(T) + PAD_IDX + 1)
     tap("prenet_out", h)
 
+    return _wrapped_encoder(sd, h, n_layers, tap)
+
+
+def _wrapped_encoder(sd, h: torch.Tensor, n_layers, tap) -> torch.Tensor:
+    """SpeechT5Encoder.forward (HF:1250-1338) on one unpadded sequence h f32[T, 768] -- shared by the speech and text paths."""
+    T = h.shape[0]
     # --- a10: encoder input LayerNorm, HF:1292 ----------------------------------------------------
     e = "wrapped_encoder."
     h = F.layer_norm(h, (HIDDEN,), sd[e + "layer_norm.weight"], sd[e + "layer_norm.bias"], EPS)
@@ -177,6 +183,31 @@ def encode_utterance(sd: Dict[str, torch.Tensor], wave: torch.Tensor, n_layers: 
         h = F.layer_norm(h + ff, (HIDDEN,), sd[lp + "final_layer_norm.weight"], sd[lp + "final_layer_norm.bias"], EPS)
         tap(f"layer{l}", h)
     return h
+
+
+
+
+def scaled_positional_rows(n: int, dim: int = HIDDEN) -> torch.Tensor:
+    """SpeechT5ScaledPositionalEncoding table rows 0..n-1 (HF:405-411): sin on even, cos on odd columns."""
+    position = torch.arange(0, n).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, dim, 2, dtype=torch.int64).float() * -(math.log(10000.0) / dim))
+    pe = torch.zeros(n, dim)
+    pe[:, 0::2] = torch.sin(position.float() * div_term)
+    pe[:, 1::2] = torch.cos(position.float() * div_term)
+    return pe
+
+
+def encode_text(sd: Dict[str, torch.Tensor], token_ids: torch.Tensor, n_layers: Optional[int] = None,
+                taps: Optional[dict] = None) -> torch.Tensor:
+    """Text-modality encoder for one unpadded token sequence: i64[T] -> last_hidden_state f32[T, 768].
+    SpeechT5EncoderWithTextPrenet (HF:1377-1415): SpeechT5TextEncoderPrenet (embed_tokens, HF:776-779; emb + alpha * pe[:T],
+    HF:418-421) then the wrapped encoder; the reference calls it at extract_speecht5_base_embeddings_slurp.py:88."""
+    sd = _strip(sd)
+    tap = (lambda k, v: taps.__setitem__(k, v.detach().clone())) if taps is not None else (lambda k, v: None)
+    emb = sd["prenet.embed_tokens.weight"][token_ids.long()]
+    h = emb + sd["prenet.encode_positions.alpha"] * scaled_positional_rows(emb.shape[0])
+    tap("prenet_out", h)
+    return _wrapped_encoder(sd, h, n_layers, tap)
 
 
 def position_bias_reference_form(sd, qh: torch.Tensor) -> torch.Tensor:
