@@ -75,6 +75,30 @@ def read_slurp_index(data_path: str, split: str, modality: str = "audio"):
     return items
 
 
+def load_weights_file(path: str):
+    """HF-keyed state dict from a checkpoint file: ``model.safetensors`` (what ``microsoft/speecht5_asr`` ships), a torch
+    ``.bin`` / ``.pt`` file, or one of the reference's pickles (map_speecht5_hf.py output).  Decoder / head tensors of a
+    full-model checkpoint are skipped later by the encoder's loader."""
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path, device="cpu")
+    if path.endswith(".pickle") or path.endswith(".pkl"):
+        with open(path, "rb") as fh:
+            return pickle.load(fh)
+    import torch
+    sd = torch.load(path, map_location="cpu")
+    return sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+
+
+def zero_mean_unit_var(x: np.ndarray) -> np.ndarray:
+    """``do_normalize=True`` of SpeechT5FeatureExtractor (HF feature_extraction_speecht5.py:119-137):
+    (x - mean) / sqrt(var + 1e-7) over the utterance's own samples.  The processor's default is False; the encoder output
+    barely depends on it (conv0 has no bias and its GroupNorm renormalises every channel over time), but it is the
+    reference's preprocessing switch, so it is offered."""
+    x = np.asarray(x, dtype=np.float32)
+    return ((x - x.mean()) / np.sqrt(x.var() + 1e-7)).astype(np.float32)
+
+
 def load_audio(path: str) -> np.ndarray:
     """Decode + resample to 16 kHz mono float32 (reference: ``librosa.load(path, sr=16000)``, :55-57)."""
     try:
@@ -232,6 +256,7 @@ def main(argv=None):
     p.add_argument("--synthetic", type=int, default=0, help="use N synthetic SLURP-shaped utterances and random-init weights")
     p.add_argument("--device", default="cuda:0")
     p.add_argument("--max-frames", type=int, default=65536)
+    p.add_argument("--do-normalize", action="store_true", help="zero-mean / unit-variance waveforms (the feature extractor's do_normalize)")
     p.add_argument("--tokenizer", default="microsoft/speecht5_asr", help="text modality: SpeechT5 tokenizer name or local directory")
     a = p.parse_args(argv)
     print(f"Extracting {a.modality} embeddings from SLURP {a.split} set using SpeechT5 (loco_asr_b200)")
@@ -259,8 +284,7 @@ def main(argv=None):
     else:
         classes = load_classes(a.classes_file)
         if a.weights:
-            sd = torch.load(a.weights, map_location="cpu") if not a.weights.endswith(".pickle") else pickle.load(open(a.weights, "rb"))
-            enc.load_state_dict(sd)
+            enc.load_state_dict(load_weights_file(a.weights))
         else:
             with open(os.path.join(a.mapping_dir, "encoder_state_dict.pickle"), "rb") as fh:
                 enc.wrapped_encoder.load_state_dict(pickle.load(fh))
@@ -269,6 +293,9 @@ def main(argv=None):
                 enc.prenet.load_state_dict(pickle.load(fh))
         items = read_slurp_index(a.data_path, a.split, a.modality)
         waves_fn = load_tokenizer(a.tokenizer) if text else load_audio
+    if a.do_normalize and not text:
+        raw_fn = waves_fn
+        waves_fn = lambda key: zero_mean_unit_var(raw_fn(key))
     enc.finalize()
     print(f"{a.split} set size: {len(items)}")
     folder = output_folder(a.out_root, a.version, a.split, a.modality)

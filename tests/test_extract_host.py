@@ -73,3 +73,29 @@ def test_masked_head_equals_reference_classifier_on_unpadded_input():
             ref = torch.nn.functional.linear(pooled, w, b)[0, 0]
             assert torch.allclose(got[u], ref, atol=1e-5), method
             off += t
+
+
+def test_weight_file_loaders_round_trip(tmp_path):
+    """--weights accepts safetensors (the hub format of microsoft/speecht5_asr), torch files and the reference's pickles."""
+    import pickle
+    import torch
+    from safetensors.torch import save_file
+    from loco_asr_b200 import extract
+    sd = {"speecht5.encoder.wrapped_encoder.layer_norm.weight": torch.arange(768, dtype=torch.float32),
+          "speecht5.decoder.something": torch.ones(3)}
+    save_file(sd, str(tmp_path / "model.safetensors"))
+    torch.save(sd, str(tmp_path / "pytorch_model.bin"))
+    with open(tmp_path / "encoder_state_dict.pickle", "wb") as fh:
+        pickle.dump(sd, fh)
+    for name in ("model.safetensors", "pytorch_model.bin", "encoder_state_dict.pickle"):
+        got = extract.load_weights_file(str(tmp_path / name))
+        assert set(got) == set(sd) and torch.equal(got["speecht5.encoder.wrapped_encoder.layer_norm.weight"], sd["speecht5.encoder.wrapped_encoder.layer_norm.weight"])
+
+
+def test_do_normalize_matches_hf_feature_extractor():
+    from transformers import SpeechT5FeatureExtractor
+    from loco_asr_b200 import extract
+    x = (np.random.default_rng(0).standard_normal(4000) * 0.3 + 0.1).astype(np.float32)
+    fe = SpeechT5FeatureExtractor(do_normalize=True)
+    ref = fe(audio=[x], sampling_rate=16000, return_tensors="np")["input_values"][0]
+    np.testing.assert_allclose(extract.zero_mean_unit_var(x), ref, atol=1e-5)
