@@ -146,6 +146,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: a failed probe parks the warp (NANOSLEEP.SYNCS: until the barrier's phase completes or
+// `ns` nanoseconds pass) instead of returning after ~50 cycles, so a waiting warp stops competing for issue slots with the
+// warps doing the work -- it matters in the persistent kernels, whose idle roles would otherwise poll at full speed.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 // Bounded spin: a protocol bug traps (surfacing as a CUDA error at the next sync) instead of hanging
 // the GPU box.  The bound is minutes of wall clock, far beyond any legitimate wait.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
