@@ -45,6 +45,7 @@ def parse_args():
     p.add_argument("--cpu-sample", type=int, default=96, help="utterances in the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--seed", type=int, default=1234)
+    p.add_argument("--no-stage-events", action="store_true", help="debug: time the steps without the per-launch CUDA events (no roofline)")
     p.add_argument("--attn-impl", type=int, default=-1, help="debug: force attention kernel (0 tcgen05, 1 mma.sync)")
     p.add_argument("--workload", choices=["slurp", "long30", "long60"], default="slurp",
                    help="slurp = BASELINE configs[1] (the metric's workload); long30/long60 = configs[3] (256 x 30 s / 128 x 60 s)")
@@ -208,7 +209,7 @@ def main():
         dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    enc.profile_enable(True)
+    enc.profile_enable(not args.no_stage_events)
     launches0 = enc.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()

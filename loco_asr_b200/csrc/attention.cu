@@ -53,6 +53,8 @@ __device__ __forceinline__ void load_tile32(bf16* dst, const bf16* src, int64_t 
 __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ pe_k,
                                                         const UttMeta* __restrict__ meta, const int32_t* __restrict__ utt_index,
                                                         bf16* __restrict__ ctx, int qt_cols) {
+    pdl_launch_dependents();
+    pdl_wait();
     const UttMeta m = meta[utt_index != nullptr ? utt_index[blockIdx.z] : (int)blockIdx.z];
     const int T = m.t6;
     const int i0 = blockIdx.x * AQ;
@@ -309,8 +311,7 @@ int launch_attention(const bf16* qkv, const bf16* pe_k, const UttMeta* meta, con
     if (n_utts <= 0 || max_t6 <= 0) return 0;
     const int qt_cols = qt_cols_for(max_t6);
     dim3 grid((max_t6 + AQ - 1) / AQ, kHeads, n_utts);
-    attention_kernel<<<grid, 128, attn_smem_bytes(qt_cols), s>>>(qkv, pe_k, meta, utt_index, ctx, qt_cols);
-    return (int)cudaGetLastError();
+    return launch_pdl(attention_kernel, grid, dim3(128), (size_t)attn_smem_bytes(qt_cols), s, qkv, pe_k, meta, utt_index, ctx, qt_cols);
 }
 
 }  // namespace loco

@@ -182,6 +182,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
+    pdl_launch_dependents();
+    pdl_wait();          // the prologue above overlapped the previous kernel's tail; nothing before this line touches global data
 
     if (warp == WARP_LOAD || warp == WARP_LOAD + 1) {
         // ===================== loaders: one per group (group 0's also brings pe_k and the Q tiles) =====================
@@ -640,9 +642,8 @@ int launch_attention_tc(const void* qkv_map, const void* pe_map, const PcTile* t
     if (n_tiles <= 0) return 0;
     const int n_items = n_tiles * kHeads;
     const int grid = n_items < num_sms ? n_items : num_sms;
-    attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, s>>>(*reinterpret_cast<const CUtensorMap*>(qkv_map),
-                                                          *reinterpret_cast<const CUtensorMap*>(pe_map), tiles, n_items, ctx);
-    int rc = (int)cudaGetLastError();
+    int rc = launch_pdl(attention_tc_kernel, dim3(grid), dim3(FA_THREADS), (size_t)FA_SMEM, s, *reinterpret_cast<const CUtensorMap*>(qkv_map),
+                        *reinterpret_cast<const CUtensorMap*>(pe_map), tiles, n_items, ctx);
     static const bool debug = getenv("LOCO_ATTN_DEBUG") != nullptr;
     if (debug && !rc) {
         int t[17] = {0};

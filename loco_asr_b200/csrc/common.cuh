@@ -117,6 +117,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch (opt-in, LOCO_PDL=1, see launch_pdl in internal.h; both are no-ops in a normal launch): launch_dependents lets the NEXT kernel's CTAs be scheduled as soon as SM resources free up, so
+// its launch latency and prologue (barrier init, TMEM allocation, tensor-map prefetch) overlap this kernel's tail wave;
+// wait blocks until the PREVIOUS kernel has completed and its memory is visible -- it must precede every global access.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier / TMA / tcgen05 PTX wrappers
 // ---------------------------------------------------------------------------------------------

@@ -22,6 +22,8 @@ constexpr int kNumMoments = 65;    // 10 first + 55 second moments
 
 __global__ void __launch_bounds__(256) wave_moments_kernel(const float* __restrict__ wave, const UttMeta* __restrict__ meta,
                                                             double* __restrict__ partial, int chunks) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int u = blockIdx.y, chunk = blockIdx.x;
     const UttMeta m = meta[u];
     const int f0 = chunk * kStatFrames;
@@ -71,6 +73,8 @@ __global__ void __launch_bounds__(512) gn_finalize_kernel(const double* __restri
                                                            const UttMeta* __restrict__ meta, const float* __restrict__ w0,
                                                            const float* __restrict__ gn_w, const float* __restrict__ gn_b,
                                                            float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int u = blockIdx.x;
     __shared__ double mom[kNumMoments];
     if (threadIdx.x < kNumMoments) {
@@ -128,6 +132,8 @@ __device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
 __global__ void __launch_bounds__(C0_WARPS * 32) conv0_mma_kernel(const float* __restrict__ wave, const UttMeta* __restrict__ meta,
                                                                    const float* __restrict__ w0, const float* __restrict__ scale,
                                                                    const float* __restrict__ shift, bf16* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int u = blockIdx.y;
     const UttMeta m = meta[u];
     const int slot0 = m.slot6 << 6;
@@ -244,17 +250,16 @@ int wave_stats_chunks(int max_t0) { return max_t0 <= 0 ? 1 : (max_t0 + kStatFram
 int launch_wave_stats(const float* wave, const UttMeta* meta, int n_utts, int chunks, const float* w0, const float* gn_w,
                       const float* gn_b, double* partial, float* scale, float* shift, cudaStream_t s) {
     if (n_utts <= 0) return 0;
-    wave_moments_kernel<<<dim3(chunks, n_utts), 256, 0, s>>>(wave, meta, partial, chunks);
-    gn_finalize_kernel<<<n_utts, 512, 0, s>>>(partial, chunks, meta, w0, gn_w, gn_b, scale, shift);
-    return (int)cudaGetLastError();
+    int rc = launch_pdl(wave_moments_kernel, dim3(chunks, n_utts), dim3(256), 0, s, wave, meta, partial, chunks);
+    if (rc) return rc;
+    return launch_pdl(gn_finalize_kernel, dim3(n_utts), dim3(512), 0, s, partial, chunks, meta, w0, gn_w, gn_b, scale, shift);
 }
 
 int launch_conv0(const float* wave, const UttMeta* meta, int n_utts, int max_slot0, const float* w0, const float* scale,
                  const float* shift, bf16* out, cudaStream_t s) {
     if (n_utts <= 0) return 0;
     dim3 grid((max_slot0 + C0_FRAMES - 1) / C0_FRAMES, n_utts);
-    conv0_mma_kernel<<<grid, C0_WARPS * 32, C0_SMEM, s>>>(wave, meta, w0, scale, shift, out);
-    return (int)cudaGetLastError();
+    return launch_pdl(conv0_mma_kernel, grid, dim3(C0_WARPS * 32), (size_t)C0_SMEM, s, wave, meta, w0, scale, shift, out);
 }
 
 }  // namespace loco

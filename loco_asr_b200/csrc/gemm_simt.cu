@@ -14,6 +14,8 @@ template <int EPI>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restrict__ W,
                                                         bf16* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
                                                         const bf16* __restrict__ R, int64_t ldr, int M, int N, int K) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sa[TK][TM + 1];
     __shared__ float sb[TK][TN + 1];
     const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
@@ -64,13 +66,13 @@ int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream) {
     dim3 grid((g.M + TM - 1) / TM, g.N / TN);
     switch (g.epilogue) {
         case EPI_BIAS:
-            gemm_simt_kernel<EPI_BIAS><<<grid, 256, 0, stream>>>(g.A, g.lda, g.W, g.C, g.ldc, g.bias, g.R, g.ldr, g.M, g.N, g.K);
+            launch_pdl(gemm_simt_kernel<EPI_BIAS>, grid, dim3(256), 0, stream, g.A, g.lda, g.W, g.C, g.ldc, g.bias, g.R, g.ldr, g.M, g.N, g.K);
             break;
         case EPI_BIAS_GELU:
-            gemm_simt_kernel<EPI_BIAS_GELU><<<grid, 256, 0, stream>>>(g.A, g.lda, g.W, g.C, g.ldc, g.bias, g.R, g.ldr, g.M, g.N, g.K);
+            launch_pdl(gemm_simt_kernel<EPI_BIAS_GELU>, grid, dim3(256), 0, stream, g.A, g.lda, g.W, g.C, g.ldc, g.bias, g.R, g.ldr, g.M, g.N, g.K);
             break;
         case EPI_BIAS_RESIDUAL:
-            gemm_simt_kernel<EPI_BIAS_RESIDUAL><<<grid, 256, 0, stream>>>(g.A, g.lda, g.W, g.C, g.ldc, g.bias, g.R, g.ldr, g.M, g.N, g.K);
+            launch_pdl(gemm_simt_kernel<EPI_BIAS_RESIDUAL>, grid, dim3(256), 0, stream, g.A, g.lda, g.W, g.C, g.ldc, g.bias, g.R, g.ldr, g.M, g.N, g.K);
             break;
         default: return (int)cudaErrorInvalidValue;
     }

@@ -33,6 +33,26 @@ struct GemmArgs {
     int epilogue;
 };
 
+// Launch helper.  With LOCO_PDL=1 kernels are launched with programmatic stream serialization (PDL): a kernel may be
+// scheduled while its predecessor in the stream drains and blocks in pdl_wait() (griddepcontrol.wait) until the predecessor
+// has completed.  OFF by default: on the SLURP-shaped bench it measured 1.7 % slower (the persistent kernels leave no SM
+// resources for an early successor, so only the wait's own latency is added).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // tcgen05/TMEM/TMA GEMM (gemm_tcgen05.cu).  Returns cudaError as int (0 = ok).
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
 int gemm_tc_launch(const GemmArgs& g, int num_sms, cudaStream_t stream);

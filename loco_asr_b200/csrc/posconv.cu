@@ -35,6 +35,8 @@ __device__ __forceinline__ void load_w_stage(bf16* sw, const bf16* wg, int chunk
 __global__ void __launch_bounds__(128) posconv_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w,
                                                       const float* __restrict__ bias, const UttMeta* __restrict__ meta,
                                                       bf16* __restrict__ pc) {
+    pdl_launch_dependents();
+    pdl_wait();
     const UttMeta m = meta[blockIdx.z];
     const int f0 = blockIdx.x * PC_ROWS;
     if (f0 >= m.t6) return;
@@ -123,8 +125,7 @@ int launch_posconv(const bf16* h, const bf16* w, const float* bias, const UttMet
                    cudaStream_t s) {
     if (n_utts <= 0 || max_t6 <= 0) return 0;
     dim3 grid((max_t6 + PC_ROWS - 1) / PC_ROWS, kPosGroups, n_utts);
-    posconv_kernel<<<grid, 128, PC_SMEM, s>>>(h, w, bias, meta, pc);
-    return (int)cudaGetLastError();
+    return launch_pdl(posconv_kernel, grid, dim3(128), (size_t)PC_SMEM, s, h, w, bias, meta, pc);
 }
 
 }  // namespace loco

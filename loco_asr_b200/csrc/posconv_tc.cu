@@ -64,6 +64,8 @@ posconv_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w, const 
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), PT_TMEM_COLS);
+    pdl_launch_dependents();
+    pdl_wait();          // barrier init / TMEM allocation overlap the previous kernel's tail
 
     // ---- stage the input windows (all threads): frames f0-64 .. f0+190, zero outside [0, t6) ----------------
     for (int t = 0; t < my_tiles; ++t) {
@@ -187,8 +189,7 @@ int posconv_tc_init() {
 int launch_posconv_tc(const bf16* h, const bf16* w_tc, const float* bias, const PcTile* tiles, int n_tiles, bf16* pc, cudaStream_t s) {
     if (n_tiles <= 0) return 0;
     dim3 grid((n_tiles + PT_TILES - 1) / PT_TILES, kPosGroups);
-    posconv_tc_kernel<<<grid, PT_THREADS, PT_SMEM, s>>>(h, w_tc, bias, tiles, n_tiles, pc);
-    return (int)cudaGetLastError();
+    return launch_pdl(posconv_tc_kernel, grid, dim3(PT_THREADS), (size_t)PT_SMEM, s, h, w_tc, bias, tiles, n_tiles, pc);
 }
 
 }  // namespace loco

@@ -102,6 +102,8 @@ template <int COLS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -115,6 +117,8 @@ __global__ void __launch_bounds__(256) prenet_ln_kernel(const bf16* __restrict__
                                                          const float* __restrict__ sin_table, const int32_t* __restrict__ row_frame,
                                                          bf16* __restrict__ y, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -140,6 +144,8 @@ __global__ void __launch_bounds__(256) text_prenet_ln_kernel(const int32_t* __re
                                                               const float* __restrict__ pe, float alpha, int vocab,
                                                               const int32_t* __restrict__ row_frame, bf16* __restrict__ y,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta, int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -168,6 +174,8 @@ __global__ void __launch_bounds__(256) text_prenet_ln_kernel(const int32_t* __re
 __global__ void __launch_bounds__(256) final_ln_pool_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const UttMeta* __restrict__ meta,
                                                              float* __restrict__ pooled, float* __restrict__ hidden_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int u = blockIdx.x;
     const UttMeta m = meta[u];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -199,6 +207,8 @@ __global__ void __launch_bounds__(256) final_ln_pool_kernel(const bf16* __restri
 }
 
 __global__ void row_frames_kernel(const UttMeta* __restrict__ meta, int32_t* __restrict__ row_frame) {
+    pdl_launch_dependents();
+    pdl_wait();
     const UttMeta m = meta[blockIdx.y];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < m.slot6) row_frame[m.row6 + t] = t < m.t6 ? t : -1;
@@ -209,8 +219,8 @@ __global__ void row_frames_kernel(const UttMeta* __restrict__ meta, int32_t* __r
 int launch_layernorm(const bf16* x, bf16* y, const float* gamma, const float* beta, int rows, int cols, cudaStream_t s) {
     if (rows <= 0) return 0;
     const int grid = (rows + 7) / 8;
-    if (cols == kHidden) layernorm_kernel<kHidden><<<grid, 256, 0, s>>>(x, y, gamma, beta, rows);
-    else if (cols == kConvDim) layernorm_kernel<kConvDim><<<grid, 256, 0, s>>>(x, y, gamma, beta, rows);
+    if (cols == kHidden) return launch_pdl(layernorm_kernel<kHidden>, dim3(grid), dim3(256), 0, s, x, y, gamma, beta, rows);
+    else if (cols == kConvDim) return launch_pdl(layernorm_kernel<kConvDim>, dim3(grid), dim3(256), 0, s, x, y, gamma, beta, rows);
     else return (int)cudaErrorInvalidValue;
     return (int)cudaGetLastError();
 }
@@ -218,28 +228,24 @@ int launch_layernorm(const bf16* x, bf16* y, const float* gamma, const float* be
 int launch_prenet_ln(const bf16* h, const bf16* pc, const float* sin_table, const int32_t* row_frame, bf16* y,
                      const float* gamma, const float* beta, int rows, cudaStream_t s) {
     if (rows <= 0) return 0;
-    prenet_ln_kernel<<<(rows + 7) / 8, 256, 0, s>>>(h, pc, sin_table, row_frame, y, gamma, beta, rows);
-    return (int)cudaGetLastError();
+    return launch_pdl(prenet_ln_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, h, pc, sin_table, row_frame, y, gamma, beta, rows);
 }
 
 int launch_text_prenet_ln(const int32_t* tokens, const float* embed, const float* pe, float alpha, int vocab, const int32_t* row_frame,
                           bf16* y, const float* gamma, const float* beta, int rows, cudaStream_t s) {
     if (rows <= 0) return 0;
-    text_prenet_ln_kernel<<<(rows + 7) / 8, 256, 0, s>>>(tokens, embed, pe, alpha, vocab, row_frame, y, gamma, beta, rows);
-    return (int)cudaGetLastError();
+    return launch_pdl(text_prenet_ln_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, tokens, embed, pe, alpha, vocab, row_frame, y, gamma, beta, rows);
 }
 
 int launch_final_ln_pool(const bf16* x, const float* gamma, const float* beta, const UttMeta* meta, int n_utts,
                          float* pooled, float* hidden_out_or_null, cudaStream_t s) {
     if (n_utts <= 0) return 0;
-    final_ln_pool_kernel<<<n_utts, 256, 0, s>>>(x, gamma, beta, meta, pooled, hidden_out_or_null);
-    return (int)cudaGetLastError();
+    return launch_pdl(final_ln_pool_kernel, dim3(n_utts), dim3(256), 0, s, x, gamma, beta, meta, pooled, hidden_out_or_null);
 }
 
 int launch_row_frames(const UttMeta* meta, int n_utts, int max_slot6, int32_t* row_frame, cudaStream_t s) {
     if (n_utts <= 0) return 0;
-    row_frames_kernel<<<dim3((max_slot6 + 127) / 128, n_utts), 128, 0, s>>>(meta, row_frame);
-    return (int)cudaGetLastError();
+    return launch_pdl(row_frames_kernel, dim3((max_slot6 + 127) / 128, n_utts), dim3(128), 0, s, meta, row_frame);
 }
 
 }  // namespace loco
