@@ -216,6 +216,54 @@ class LocoSpeechT5Encoder:
         _lib.check(self._lib, self._h, rc, "loco_encode_host")
         return pooled_host
 
+    def encode_host_pipelined(self, batches, depth: int = 2):
+        """Bulk extraction from HOST buffers with the copies hidden behind the compute: ``batches`` yields
+        ``(wave_host f32[sum n] (pinned), n_samples[, pooled_host f32[B, 768] (pinned)])``; pooled host tensors are yielded
+        in order, one batch late.  Batch i+1's waveforms cross PCIe on a copy stream (into one of ``depth`` staging buffers)
+        while batch i is encoded on the current stream; the D2H of the pooled result follows its encode.  Same arithmetic
+        as ``encode_host`` / ``loco_encode_host`` (which serialise copy -> encode -> copy per call)."""
+        self.finalize()
+        dev = self.device
+        compute = torch.cuda.current_stream(dev)
+        copier = torch.cuda.Stream(dev)
+        stage = [None] * depth                     # device staging buffers for the waveforms
+        free_ev = [None] * depth                   # recorded on `compute` when the encode that read stage[k] was enqueued
+        pending = []                               # (done_event, pooled_host)
+        for i, item in enumerate(batches):
+            wave_host, n_samples = item[0], item[1]
+            pooled_host = item[2] if len(item) > 2 else None
+            if wave_host.device.type != "cpu" or wave_host.dtype != torch.float32 or not wave_host.is_contiguous():
+                raise _lib.LocoError("encode_host_pipelined wants contiguous float32 CPU tensors")
+            k = i % depth
+            n = wave_host.numel()
+            if stage[k] is None or stage[k].numel() < n:
+                if free_ev[k] is not None:
+                    free_ev[k].synchronize()
+                stage[k] = torch.empty(int(n * 1.1) + 16, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(copier):
+                if free_ev[k] is not None:
+                    copier.wait_event(free_ev[k])           # the encode that last read this staging buffer has finished
+                stage[k][:n].copy_(wave_host, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(copier)
+            compute.wait_event(copied)
+            pooled_dev = self.encode_packed(stage[k][:n], n_samples)
+            free_ev[k] = torch.cuda.Event()
+            free_ev[k].record(compute)
+            if pooled_host is None:
+                pooled_host = torch.empty(pooled_dev.shape, dtype=torch.float32).pin_memory()
+            pooled_host.copy_(pooled_dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(compute)
+            pending.append((done, pooled_host))
+            if len(pending) > 1:
+                ev, out = pending.pop(0)
+                ev.synchronize()
+                yield out
+        for ev, out in pending:
+            ev.synchronize()
+            yield out
+
     # ------------------------------------------------------------------ text modality (reference :79-93)
     def encode_text_packed(self, tokens: torch.Tensor, n_tokens: Sequence[int], return_hidden: bool = False):
         """tokens: int32[sum(n_tokens)] on this device, texts concatenated without padding.  Each text is encoded alone.

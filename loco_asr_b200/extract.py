@@ -162,7 +162,19 @@ def run(encoder, items, waves_fn, binarize, folder: str, full_sequence: bool = F
     targets = binarize([it[2] for it in todo])
     pool = ThreadPoolExecutor(max_workers=writers)
     futures = []
-    for idx in make_batches(lengths, max_frames=max_frames):
+    batches = make_batches(lengths, max_frames=max_frames)
+    if not full_sequence:
+        # pooled output: H2D of the next batch overlaps the encode of the current one (encode_host_pipelined)
+        def host_batches():
+            for idx in batches:
+                host = torch.from_numpy(np.concatenate([waves[i] for i in idx]))
+                yield (host.pin_memory() if torch.cuda.is_available() else host, [lengths[i] for i in idx])
+        for idx, pooled in zip(batches, encoder.encode_host_pipelined(host_batches())):
+            pooled = pooled.numpy()
+            for j, i in enumerate(idx):
+                futures.append(pool.submit(write_item, folder, todo[i][0], pooled[j:j + 1].copy(), targets[i]))
+        batches = []
+    for idx in batches:
         host = torch.from_numpy(np.concatenate([waves[i] for i in idx]))
         ns = [lengths[i] for i in idx]
         if full_sequence:

@@ -241,3 +241,16 @@ def test_attention_kernels_against_oracle(encoder, weights, impl):
     finally:
         encoder.debug_set("stop_after_layer", -1)
         encoder.debug_set("attn_impl", -1)
+
+
+def test_pipelined_host_path_equals_device_path(encoder):
+    """encode_host_pipelined (copy stream + staging buffers, results one batch late) returns, in order, exactly what the
+    device-resident call returns for each batch -- also when a later batch is larger than the staging buffer."""
+    batches = [H.make_waves([8000, 30000, 12345], seed=21), H.make_waves([64000, 9000], seed=22),
+               H.make_waves([20000] * 5, seed=23), H.make_waves([100000, 8000, 8000], seed=24)]
+    want = [H.run_encoder(encoder, w)[0] for w in batches]
+    items = [(torch.from_numpy(np.concatenate(w)).pin_memory(), [len(x) for x in w]) for w in batches]
+    got = list(encoder.encode_host_pipelined(items))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
