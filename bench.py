@@ -47,6 +47,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--seed", type=int, default=1234)
     p.add_argument("--no-stage-events", action="store_true", help="debug: time the steps without the per-launch CUDA events (no roofline)")
+    p.add_argument("--gemm-impl", type=int, default=-1, help="debug: force GEMM kernel (0 single-CTA tcgen05, 2 CTA-pair tcgen05)")
     p.add_argument("--attn-impl", type=int, default=-1, help="debug: force attention kernel (0 tcgen05, 1 mma.sync)")
     p.add_argument("--workload", choices=["slurp", "long30", "long60"], default="slurp",
                    help="slurp = BASELINE configs[1] (the metric's workload); long30/long60 = configs[3] (256 x 30 s / 128 x 60 s)")
@@ -176,6 +177,8 @@ def main():
     enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device=dev)
     if args.attn_impl >= 0:
         enc.debug_set("attn_impl", args.attn_impl)
+    if args.gemm_impl >= 0:
+        enc.debug_set("gemm_impl", args.gemm_impl)
     if args.workload == "slurp":
         lengths = slurp_shaped_lengths(args.utts, args.seed + rank)      # every rank owns a full set (weak scaling)
     else:

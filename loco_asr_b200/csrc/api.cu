@@ -82,7 +82,7 @@ struct loco_handle {
     int txt_pe_rows = 0;
     std::vector<LayerW> layers;
     // debug
-    int gemm_impl = 0;
+    int gemm_impl = 2;          // 2 = tcgen05 CTA pair [default], 0 = tcgen05 single CTA, 1 = SIMT reference
     int posconv_impl = 0;
     int attn_impl = -1;         // -1 = by length (tcgen05 from attn_tc_min_frames), 0 = tcgen05, 1 = mma.sync
     int attn_tc_min_frames = 193;   // utterances with at least this many frames use the tcgen05 attention kernel,
@@ -420,7 +420,7 @@ void prof_break(loco_handle* h) { h->prof_last_end = nullptr; }
 
 int run_gemm(loco_handle* h, const GemmArgs& g, cudaStream_t s) {
     prof_begin(h, CAT_GEMM, s);
-    int rc = h->gemm_impl == 1 ? gemm_simt_launch(g, s) : gemm_tc_launch(g, h->num_sms, s);
+    int rc = h->gemm_impl == 1 ? gemm_simt_launch(g, s) : h->gemm_impl == 2 ? gemm_tc2_launch(g, h->num_sms, s) : gemm_tc_launch(g, h->num_sms, s);
     prof_end(h, s);
     h->launches += 1;
     if (rc) return fail(h, LOCO_ERR_CUDA, std::string("gemm launch failed: ") + cudaGetErrorString((cudaError_t)rc));
@@ -522,6 +522,7 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     int rc = gemm_tc_init();
+    if (!rc) rc = gemm_tc2_init();
     if (!rc) rc = attention_init();
     if (!rc) rc = attention_tc_init();
     if (!rc) rc = posconv_init();

@@ -59,6 +59,9 @@ int gemm_tc_launch(const GemmArgs& g, int num_sms, cudaStream_t stream);
 // 2-D bf16 tensor map, box = [64 elements (128 B), box_rows], SWIZZLE_128B (gemm_tcgen05.cu owns the driver entry point).
 int make_tensor_map_bf16_sw128(void* map /*CUtensorMap*/, const void* base, uint64_t inner, uint64_t rows,
                                uint64_t row_stride_elems, uint32_t box_rows);
+// CTA-pair variant (gemm_tcgen05_2cta.cu): tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA loads half of the weight tile.
+int gemm_tc2_init();
+int gemm_tc2_launch(const GemmArgs& g, int num_sms, cudaStream_t stream);
 // Debug-only SIMT reference GEMM (gemm_simt.cu): used by the tests to cross-check the tensor path.
 int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);
 

@@ -40,11 +40,13 @@ def _make(M, N, K, epi, conv_like, seed):
     return a_arg, lda, w, bias, res, ref
 
 
+@pytest.mark.parametrize("impl", [2, 0], ids=["cta_pair", "single_cta"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"M{c[0]}_N{c[1]}_K{c[2]}_e{c[3]}{'_conv' if c[4] else ''}")
-def test_tcgen05_gemm_matches_fp32_reference(encoder, case):
+def test_tcgen05_gemm_matches_fp32_reference(encoder, case, impl):
+    """Both tcgen05 kernels: the CTA-pair product path (cta_group::2, 256 x 256 tiles) and the single-CTA kernel."""
     M, N, K, epi, conv_like = case
     a, lda, w, bias, res, ref = _make(M, N, K, epi, conv_like, seed=M + N + K)
-    c = encoder.debug_gemm(a, w, bias=bias, residual=res, epilogue=epi, impl=0, lda=lda, m=M)
+    c = encoder.debug_gemm(a, w, bias=bias, residual=res, epilogue=epi, impl=impl, lda=lda, m=M)
     torch.cuda.synchronize()
     err = (c.float() - ref).abs()
     tol = ref.abs() * 2 ** -8 + 2e-3            # bf16 output rounding (+ accumulation-order slack)
@@ -55,6 +57,6 @@ def test_tcgen05_gemm_matches_fp32_reference(encoder, case):
 
 def test_gemm_without_bias(encoder):
     a, lda, w, _, _, _ = _make(300, 512, 1536, _lib.EPI_BIAS_GELU, False, seed=5)
-    c = encoder.debug_gemm(a, w, bias=None, epilogue=_lib.EPI_BIAS_GELU, impl=0)
+    c = encoder.debug_gemm(a, w, bias=None, epilogue=_lib.EPI_BIAS_GELU, impl=2)
     ref = torch.nn.functional.gelu(a.float() @ w.float().t())
     assert float((c.float() - ref).abs().max()) < 0.03

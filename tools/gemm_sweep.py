@@ -9,6 +9,7 @@ from loco_asr_b200.encoder import LocoSpeechT5Encoder
 from loco_asr_b200.synth import synth_state_dict
 
 enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device="cuda:0")
+IMPL = int(os.environ.get("GEMM_IMPL", "0"))      # 0 = tcgen05 single-CTA, 2 = CTA-pair (cta_group::2)
 R = 64400
 SHAPES = [  # name, M, N, K, epilogue, conv-like
     ("conv1", R * 32, 512, 1536, _lib.EPI_BIAS_GELU, True), ("conv2", R * 16, 512, 1536, _lib.EPI_BIAS_GELU, True),
@@ -30,12 +31,12 @@ for name, M, N, K, epi, conv in SHAPES:
     res = [torch.randn(M, N, device="cuda", generator=g).bfloat16() for _ in range(nbuf)] if epi == _lib.EPI_BIAS_RESIDUAL else [None] * nbuf
     reps = 12 if M > 500000 else 36
     for _ in range(3):
-        enc.debug_gemm(a[0], w, bias=bias, residual=res[0], epilogue=epi, impl=0, lda=lda, m=M)
+        enc.debug_gemm(a[0], w, bias=bias, residual=res[0], epilogue=epi, impl=IMPL, lda=lda, m=M)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(reps):
-        enc.debug_gemm(a[i % nbuf], w, bias=bias, residual=res[i % nbuf], epilogue=epi, impl=0, lda=lda, m=M)
+        enc.debug_gemm(a[i % nbuf], w, bias=bias, residual=res[i % nbuf], epilogue=epi, impl=IMPL, lda=lda, m=M)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
