@@ -1,7 +1,7 @@
 // CTA-pair variant of the tcgen05 GEMM (gemm_tcgen05.cu): clusters of two CTAs on one TPC run `tcgen05.mma.cta_group::2`
 // on a 256 (M) x 256 (N) x 64 (K) tile.  Each CTA loads its own 128 rows of A and HALF of the B tile (128 of the 256 weight
 // rows); the pair's tensor cores read both halves, so the B operand's L2 -> shared-memory traffic and shared-memory footprint
-// per CTA halve (32 KB per stage -> 6 stages instead of 4), which is what the power-capped GEMMs of this encoder need:
+// per CTA halve (32 KB per stage; 5 stages + two staging panels per epilogue warp), which is what the power-capped GEMMs of this encoder need:
 // fewer bytes moved per FLOP.  Each CTA keeps the accumulator of its own 128 rows in its own TMEM and runs the same epilogue
 // as the single-CTA kernel.
 //
@@ -11,7 +11,8 @@
 //   empty[s]       in BOTH CTAs: multicast tcgen05.commit from the leader once the MMAs that read the stage have retired
 //   tmem_full[a]   in BOTH CTAs: multicast commit after the tile's last MMA
 //   tmem_empty[a]  on the leader: 2 x 256 arrivals, the peer's epilogue threads arrive remotely
-// Selected with loco_debug_set("gemm_impl", 2) while it is being evaluated; see tools/gemm_sweep.py for the A/B numbers.
+// The default GEMM (loco_debug_set("gemm_impl", 0) selects the single-CTA kernel); tools/gemm_sweep.py / bench.py --gemm-impl
+// for the A/B numbers: in the SLURP-shaped step the GEMM time drops 14.9 -> 14.4 ms.
 #include <stdio.h>
 
 #include "common.cuh"
@@ -24,7 +25,14 @@ namespace {
 constexpr int BM = 128;                 // rows per CTA (256 per pair)
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 6;
+#ifndef G2_STAGES
+#define G2_STAGES 5
+#endif
+#ifndef G2_PANELS
+#define G2_PANELS 2
+#endif
+constexpr int STAGES = G2_STAGES;
+constexpr int PANELS = G2_PANELS;         // staging panels per epilogue warp (2: the tile's two 64-column halves never wait on each other)
 constexpr int A_STAGE_BYTES = BM * BK * 2;         // 16 KB
 constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;   // 16 KB: this CTA's half of the weight tile
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -33,7 +41,8 @@ constexpr int TMEM_COLS = ACC_STAGES * BN;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int PANEL_BYTES = 32 * 128;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * PANEL_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PANELS * NUM_EPI_WARPS * PANEL_BYTES + 1024 + 256;
+static_assert(SMEM_BYTES <= 232448, "gemm_tc2: shared memory budget");
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address -> the pair's leader
 
 struct __align__(8) Barriers2 {
@@ -91,7 +100,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-    Barriers2* bars = reinterpret_cast<Barriers2*>(smem_aligned + STAGES * STAGE_BYTES + NUM_EPI_WARPS * PANEL_BYTES);
+    Barriers2* bars = reinterpret_cast<Barriers2*>(smem_aligned + STAGES * STAGE_BYTES + PANELS * NUM_EPI_WARPS * PANEL_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -125,6 +134,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     cluster_sync_all();                  // ... and both accumulators are allocated before the leader's first MMA
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -177,8 +188,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         // ===================== epilogue (both CTAs): this CTA's 128 rows of the pair's tile =====================
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
-        const uint32_t panel = smem_base + STAGES * STAGE_BYTES + (warp - 4) * PANEL_BYTES;
-        const uint32_t my_row = panel + lane * 128;
+        const uint32_t panel0 = smem_base + STAGES * STAGE_BYTES + (warp - 4) * PANELS * PANEL_BYTES;
         const uint32_t res_bar = smem_u32(&bars->res_full[warp - 4]);
         uint32_t res_phase = 0;
         int acc = 0;
@@ -186,15 +196,35 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         for (int tile = pair; tile < n_tiles; tile += n_pairs) {
             const int m0 = (tile / n_tiles_n) * (2 * BM) + (int)rank * BM + q * 32;
             const int n0 = (tile % n_tiles_n) * BN + half * (BN / 2);
+            if (EPI == EPI_BIAS_RESIDUAL && PANELS == 2) {
+                // both residual panels of this warp's 32 x 128 slice, fetched while the tile's MMAs still run
+                if (lane == 0) {
+                    bulk_wait_read<0>();            // the previous tile's stores have finished reading the panels
+                    mbar_arrive_expect_tx(res_bar, 2 * PANEL_BYTES);
+                    tma_load_2d(panel0, &tma_r, res_bar, n0, m0);
+                    tma_load_2d(panel0 + PANEL_BYTES, &tma_r, res_bar, n0 + 64, m0);
+                }
+                __syncwarp();
+            }
             mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
             uint32_t v[2][32];
             tmem_ld_32x32(t_row, v[0]);
+            if (EPI == EPI_BIAS_RESIDUAL && PANELS == 2) {
+                mbar_wait(res_bar, res_phase);
+                res_phase ^= 1u;
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                if ((c & 1) == 0) {
-                    if (lane == 0) bulk_wait_read<0>();
+                const uint32_t panel = panel0 + (PANELS == 2 ? (c >> 1) * PANEL_BYTES : 0);
+                const uint32_t my_row = panel + lane * 128;
+                if ((c & 1) == 0 && (PANELS == 1 || EPI != EPI_BIAS_RESIDUAL)) {
+                    // the TMA store that last read this panel must have finished before it is overwritten
+                    if (lane == 0) {
+                        if (PANELS == 2) bulk_wait_read<1>();      // only the OTHER panel's store (the most recent group) may be in flight
+                        else bulk_wait_read<0>();
+                    }
                     __syncwarp();
                     if (EPI == EPI_BIAS_RESIDUAL && lane == 0) {
                         mbar_arrive_expect_tx(res_bar, PANEL_BYTES);
@@ -208,7 +238,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                     tc_fence_before();
                     mbar_arrive_cluster(smem_u32(&bars->tmem_empty[acc]) & kPeerMask);      // the leader's barrier
                 }
-                if (EPI == EPI_BIAS_RESIDUAL && (c & 1) == 0) {
+                if (EPI == EPI_BIAS_RESIDUAL && PANELS == 1 && (c & 1) == 0) {
                     mbar_wait(res_bar, res_phase);
                     res_phase ^= 1u;
                 }
