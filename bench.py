@@ -260,14 +260,14 @@ def main():
     # DRAM bytes per GEMM launch come from the committed ncu capture of the same command (profiles/), never from this run
     gemm_traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01c_gemm_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r01d_gemm_traffic.json")) as fh:
             tj = json.load(fh)
         gemm_traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"]
     except (OSError, KeyError, ValueError):
         pass
     achieved = fl["gemm"] / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak = peaks["tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMEM/TMA bf16 GEMM, all epilogues)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel (CTA-pair tcgen05/TMEM/TMA bf16 GEMM, cta_group::2, all epilogues)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "traffic": gemm_traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)" if gemm_traffic else None,
