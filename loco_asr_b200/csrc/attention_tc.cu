@@ -40,8 +40,9 @@
 // by two phases of its barrier (see ga_empty / o_full).  Set LOCO_ATTN_DEBUG=1 to have a stuck wait reported per role.
 //
 // Measured (tools/attn_sweep.py, 64k frames per batch, per layer): 0.36 ms at T = 256, 0.51 ms at 499, 0.95 ms at 1499,
-// 1.59 ms at 2999 (384 TFLOP/s of Q K^T + P V + table FLOPs) -- 1.5-1.95x the mma.sync kernel; below ~176 frames the
-// per-item fixed costs (drain, epilogue, ~10 barrier hand-offs) dominate and the mma.sync kernel (attention.cu) is used.
+// 1.59 ms at 2999 (384 TFLOP/s of Q K^T + P V + table FLOPs) -- 1.5-1.95x the mma.sync kernel; where a 128-query tile is mostly
+// empty (< 84 or 129..192 frames) the per-item fixed costs (drain, epilogue, ~10 barrier hand-offs) dominate and the
+// mma.sync kernel (attention.cu) takes the utterance (chosen per utterance in loco_encode).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
