@@ -3,15 +3,16 @@
 // Conv1d(768 -> 768, k = 128, padding 64, groups 16), weight-norm folded at load, last frame dropped, + bias, GELU.
 //
 // Per group: out[T, 48] = X_toeplitz[T, 128*48] * W_g[128*48, 48].  The Toeplitz operand is never built.  A CTA
-// stages, for each of up to four 128-frame output tiles (any utterances), the 255-frame x 48-channel window of
+// stages, for each of up to two 128-frame output tiles (any utterances), the 255-frame x 48-channel window of
 // its inputs in shared memory in the UMMA *no-swizzle K-major* core-matrix layout with all rows 16 B apart:
 //     window[kc][row] (16 B = 8 channels),  kc = 0..5,  row = 0..255
 // so "the operand of tap j" is the same window with the descriptor start address advanced by j * 16 bytes -- 128
-// taps x 3 K-steps of tcgen05.mma (M = 128, N = 48, K = 16) read it in place, accumulating in TMEM (4 tiles x 48
+// taps x 3 K-steps of tcgen05.mma (M = 128, N = 48, K = 16) read it in place, accumulating in TMEM (2 tiles x 48
 // columns).  Frames outside the utterance are zero rows of the window: that is the conv's zero padding, and it is
 // why tiles never straddle utterances.  The group's 590 KB of weights stream ONCE per CTA (taps outer, tiles
-// inner) through a 3-stage ring filled by 1-D bulk TMA copies; with four tiles per CTA the L2 -> SM weight traffic
-// per output row is 1/8 of the mma.sync version's.
+// inner) through a 3-stage ring filled by 1-D bulk TMA copies.  Two tiles per CTA and 105 KB of shared memory put TWO CTAs on an
+// SM, so one CTA's window staging and epilogue run under the other's MMAs (four tiles per CTA and one CTA per SM halved the
+// weight traffic but left those phases exposed: 1.22 -> 1.05 ms per step).
 #include "common.cuh"
 #include "internal.h"
 
@@ -19,17 +20,20 @@ namespace loco {
 
 namespace {
 
-constexpr int PT_TILES = 4;                       // output tiles per CTA
+#ifndef PT_TILES_CFG
+#define PT_TILES_CFG 2
+#endif
+constexpr int PT_TILES = PT_TILES_CFG;            // output tiles per CTA (2: two CTAs per SM, one stages / drains while the other's MMAs run)
 constexpr int PT_ROWS = 128;                      // frames per tile (UMMA M)
 constexpr int PT_WROWS = 256;                     // window rows (255 used)
 constexpr int PT_KC = kPosGroupCh / 8;            // 6 sixteen-byte channel chunks
 constexpr int PT_WIN_BYTES = PT_KC * PT_WROWS * 16;          // 24576
 constexpr int PT_TAP_BYTES = PT_KC * kPosGroupCh * 16;       // 4608: [kc][out 48][8 in]
-constexpr int PT_STAGE_TAPS = 8;
+constexpr int PT_STAGE_TAPS = PT_TILES == 2 ? 4 : 8;
 constexpr int PT_STAGE_BYTES = PT_STAGE_TAPS * PT_TAP_BYTES; // 36864
 constexpr int PT_STAGES = 3;
 constexpr int PT_N_ITERS = kPosK / PT_STAGE_TAPS;            // 16
-constexpr int PT_TMEM_COLS = 256;                 // 4 tiles x 64-column slots (48 used)
+constexpr int PT_TMEM_COLS = PT_TILES * 64;        // 64-column slot per tile (48 used)
 constexpr int PT_THREADS = 192;                   // warp 0 weights, warp 1 MMA, warps 2-5 epilogue
 constexpr int PT_SMEM = PT_TILES * PT_WIN_BYTES + PT_STAGES * PT_STAGE_BYTES + 128 + 128;
 
@@ -40,7 +44,7 @@ struct __align__(8) PtBars {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(PT_THREADS, 1)
+__global__ void __launch_bounds__(PT_THREADS, PT_TILES == 2 ? 2 : 1)
 posconv_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w, const float* __restrict__ bias,
                   const PcTile* __restrict__ tiles, int n_tiles_total, bf16* __restrict__ pc) {
     extern __shared__ uint8_t smem_raw[];
