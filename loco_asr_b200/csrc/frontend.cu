@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(512) gn_finalize_kernel(const double* __restri
 //     so every global store is a full 128-byte line of the time-major [T0, 512] activation.
 constexpr int C0_WARPS = 8;
 constexpr int C0_FRAMES = 512;               // frames per CTA (4 passes of 8 warps x 16 frames)
-constexpr int C0_BLD = 56;                   // padded K (48) of the smem weight matrix -> conflict-free ldmatrix
+constexpr int C0_BLD = 40;                   // padded K (32: w_hi | w_lo) of the smem weight matrix -> conflict-free ldmatrix, 3 CTAs/SM
 constexpr int C0_SLD = 72;                   // staging row: 64 channels + 8 pad (bf16)
 constexpr int C0_SMEM = kConvDim * C0_BLD * 2 + (C0_FRAMES * 5 + 8) * 4 + kConvDim * 4 + C0_WARPS * 16 * C0_SLD * 2;
 
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(C0_WARPS * 32) conv0_mma_kernel(const float* _
     const int f0 = blockIdx.x * C0_FRAMES;
     if (f0 >= slot0) return;
     extern __shared__ __align__(16) uint8_t smem[];
-    bf16* sB = reinterpret_cast<bf16*>(smem);                                   // [512][56]
+    bf16* sB = reinterpret_cast<bf16*>(smem);                                   // [512][40]: w_hi taps 0..15, w_lo taps 0..15
     float* xs = reinterpret_cast<float*>(sB + kConvDim * C0_BLD);               // [512*5 + 8]
     float* ssh = xs + C0_FRAMES * 5 + 8;                                         // [512] shift
     bf16* stage = reinterpret_cast<bf16*>(ssh + kConvDim);                      // [8 warps][16][72]
@@ -156,9 +156,8 @@ __global__ void __launch_bounds__(C0_WARPS * 32) conv0_mma_kernel(const float* _
         const int c = i >> 4, k = i & 15;
         bf16 hi = __float2bfloat16_rn(0.f), lo = hi;
         if (k < 10) split_bf16(__ldg(w0 + c * 10 + k) * scale[(int64_t)u * kConvDim + c], hi, lo);
-        sB[c * C0_BLD + k] = hi;         // pairs with x_hi
-        sB[c * C0_BLD + 16 + k] = hi;    // pairs with x_lo
-        sB[c * C0_BLD + 32 + k] = lo;    // pairs with x_hi
+        sB[c * C0_BLD + k] = hi;         // pairs with x_hi, then with x_lo
+        sB[c * C0_BLD + 16 + k] = lo;    // pairs with x_hi
     }
     for (int i = tid; i < kConvDim; i += C0_WARPS * 32) ssh[i] = shift[(int64_t)u * kConvDim + i];
     __syncthreads();
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(C0_WARPS * 32) conv0_mma_kernel(const float* _
 #pragma unroll
                 for (int ks = 0; ks < 3; ++ks) {
                     uint32_t b[4];
-                    ldmatrix_x4(b, smem_u32(sB + (cg * 64 + np * 16 + b_row) * C0_BLD + ks * 16 + b_col));
+                    ldmatrix_x4(b, smem_u32(sB + (cg * 64 + np * 16 + b_row) * C0_BLD + (ks >> 1) * 16 + b_col));   // ks 0,1: w_hi; 2: w_lo
                     const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
                     if (ks == 1) {
                         mma_16816(acc[np * 2], a_lo, b0);
