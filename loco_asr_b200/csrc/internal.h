@@ -90,9 +90,21 @@ int launch_layernorm(const bf16* x, bf16* y, const float* gamma, const float* be
 // y = LayerNorm(h + pc + sinusoid(frame + 2)) : end of the prenet + encoder input LayerNorm; slot padding rows -> 0.
 int launch_prenet_ln(const bf16* h, const bf16* pc, const float* sin_table, const int32_t* row_frame, bf16* y,
                      const float* gamma, const float* beta, int rows, cudaStream_t s);
-// Final LayerNorm of the last layer fused with the masked mean-pool and the optional compact fp32 copy.
+// Classifier head fused into the final kernel (speech_text/intent_classifier.py:24-48); all pointers device, fp32.
+enum { kPoolAverage = 0, kPoolMax = 1, kPoolAttention = 2 };
+struct HeadArgs {
+    int method = kPoolAverage;
+    int n_classes = 0;
+    const float* q = nullptr;       // [768]            (self_attention only)
+    const float* w = nullptr;       // [n_classes, 768] classifier.0.weight
+    const float* b = nullptr;       // [n_classes]      classifier.0.bias
+    float* pooled_out = nullptr;    // [n_utts, 768] or null: the method's pooled vector
+    float* logits_out = nullptr;    // [n_utts, n_classes] or null
+};
+// Final LayerNorm of the last layer fused with the masked mean-pool, the optional compact fp32 copy and, when
+// `head` carries an output pointer, the classifier's pooling + Linear.
 int launch_final_ln_pool(const bf16* x, const float* gamma, const float* beta, const UttMeta* meta, int n_utts,
-                         float* pooled /*[n,768]*/, float* hidden_out_or_null, cudaStream_t s);
+                         float* pooled /*[n,768]*/, float* hidden_out_or_null, const HeadArgs& head, cudaStream_t s);
 // row_frame[r] = frame index of row r inside its utterance, or -1 for slot padding rows.
 int launch_row_frames(const UttMeta* meta, int n_utts, int max_slot6, int32_t* row_frame, cudaStream_t s);
 // text modality: y[row] = LayerNorm(embed[tokens[row]] + alpha * pe[row_frame[row]])

@@ -171,9 +171,16 @@ __global__ void __launch_bounds__(256) text_prenet_ln_kernel(const int32_t* __re
 
 // One block per utterance: LayerNorm every valid frame, accumulate column sums per warp in registers,
 // reduce across the 8 warps in a fixed order (deterministic), write mean over the utterance's T frames.
+// HEAD adds the classifier's other poolings and its Linear as the same epilogue (speech_text/intent_classifier.py):
+//   max            :28-30  max over the utterance's frames
+//   self_attention :32-36  z_t = x_t . q, alpha = softmax_t(z), sum_t alpha_t x_t   (per-warp online softmax,
+//                          the 8 partial (m, l, acc) states merged in warp order)
+//   classifier     :20-22, 48  logits = W pooled + b, pooled being the method the head was configured with
+template <bool HEAD>
 __global__ void __launch_bounds__(256) final_ln_pool_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const UttMeta* __restrict__ meta,
-                                                             float* __restrict__ pooled, float* __restrict__ hidden_out) {
+                                                             float* __restrict__ pooled, float* __restrict__ hidden_out,
+                                                             HeadArgs head) {
     pdl_launch_dependents();
     pdl_wait();
     const int u = blockIdx.x;
@@ -181,8 +188,20 @@ __global__ void __launch_bounds__(256) final_ln_pool_kernel(const bf16* __restri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NV = RowVec<kHidden>::kChunks * 8;
     float acc[NV];
+    float mx[HEAD ? NV : 1], att[HEAD ? NV : 1], qv[HEAD ? NV : 1];
+    float m_run = -INFINITY, l_run = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    if constexpr (HEAD) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) mx[i] = -INFINITY, att[i] = 0.f, qv[i] = 0.f;
+        if (head.method == kPoolAttention) {
+#pragma unroll
+            for (int c = 0; c < RowVec<kHidden>::kChunks; ++c)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) qv[c * 8 + e] = __ldg(head.q + (c * 32 + lane) * 8 + e);
+        }
+    }
     for (int t = warp; t < m.t6; t += 8) {
         RowVec<kHidden> r;
         r.load(x + (int64_t)(m.row6 + t) * kHidden, lane);
@@ -190,8 +209,27 @@ __global__ void __launch_bounds__(256) final_ln_pool_kernel(const bf16* __restri
         if (hidden_out != nullptr) r.store_f32(hidden_out + (int64_t)(m.out_row + t) * kHidden, lane);
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i] += r.v[i];
+        if constexpr (HEAD) {
+            if (head.method == kPoolMax) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) mx[i] = fmaxf(mx[i], r.v[i]);
+            } else if (head.method == kPoolAttention) {
+                float z = 0.f;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) z = fmaf(r.v[i], qv[i], z);
+                z = warp_sum(z);
+                const float m_new = fmaxf(m_run, z);
+                const float corr = __expf(m_run - m_new), p = __expf(z - m_new);   // first frame: exp(-inf) = 0
+                l_run = fmaf(l_run, corr, p);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) att[i] = fmaf(att[i], corr, p * r.v[i]);
+                m_run = m_new;
+            }
+        }
     }
     __shared__ float red[8][kHidden];
+    __shared__ float head_vec[HEAD ? kHidden : 1];
+    __shared__ float warp_m[8], warp_l[8];
 #pragma unroll
     for (int c = 0; c < RowVec<kHidden>::kChunks; ++c)
 #pragma unroll
@@ -203,6 +241,62 @@ __global__ void __launch_bounds__(256) final_ln_pool_kernel(const bf16* __restri
 #pragma unroll
         for (int w = 0; w < 8; ++w) s += red[w][col];
         pooled[(int64_t)u * kHidden + col] = s * inv;
+        if constexpr (HEAD)
+            if (head.method == kPoolAverage) head_vec[col] = s * inv;
+    }
+    if constexpr (HEAD) {
+        if (head.method != kPoolAverage) {
+            __syncthreads();
+            const bool is_max = head.method == kPoolMax;
+#pragma unroll
+            for (int c = 0; c < RowVec<kHidden>::kChunks; ++c)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) red[warp][(c * 32 + lane) * 8 + e] = is_max ? mx[c * 8 + e] : att[c * 8 + e];
+            if (lane == 0) warp_m[warp] = m_run, warp_l[warp] = l_run;
+            __syncthreads();
+            float m_all = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) m_all = fmaxf(m_all, warp_m[w]);
+            float scale[8], l_all = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                scale[w] = warp_m[w] == -INFINITY ? 0.f : __expf(warp_m[w] - m_all);    // warps that saw no frame
+                l_all = fmaf(warp_l[w], scale[w], l_all);
+            }
+            const float inv_l = l_all > 0.f ? 1.0f / l_all : 0.f;
+            for (int col = threadIdx.x; col < kHidden; col += 256) {
+                float v;
+                if (is_max) {
+                    v = -INFINITY;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) v = fmaxf(v, red[w][col]);
+                    if (m.t6 <= 0) v = 0.f;
+                } else {
+                    v = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) v = fmaf(red[w][col], scale[w], v);
+                    v *= inv_l;
+                }
+                head_vec[col] = v;
+            }
+        }
+        __syncthreads();
+        if (head.pooled_out != nullptr)
+            for (int col = threadIdx.x; col < kHidden; col += 256) head.pooled_out[(int64_t)u * kHidden + col] = head_vec[col];
+        if (head.logits_out != nullptr) {
+            for (int c = warp; c < head.n_classes; c += 8) {
+                const float* wr = head.w + (int64_t)c * kHidden;
+                float d = 0.f;
+#pragma unroll
+                for (int k = 0; k < kHidden / 128; ++k) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(wr + (k * 32 + lane) * 4));
+                    const float4 b = *reinterpret_cast<const float4*>(head_vec + (k * 32 + lane) * 4);
+                    d = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, d))));
+                }
+                d = warp_sum(d);
+                if (lane == 0) head.logits_out[(int64_t)u * head.n_classes + c] = d + __ldg(head.b + c);
+            }
+        }
     }
 }
 
@@ -238,9 +332,11 @@ int launch_text_prenet_ln(const int32_t* tokens, const float* embed, const float
 }
 
 int launch_final_ln_pool(const bf16* x, const float* gamma, const float* beta, const UttMeta* meta, int n_utts,
-                         float* pooled, float* hidden_out_or_null, cudaStream_t s) {
+                         float* pooled, float* hidden_out_or_null, const HeadArgs& head, cudaStream_t s) {
     if (n_utts <= 0) return 0;
-    return launch_pdl(final_ln_pool_kernel, dim3(n_utts), dim3(256), 0, s, x, gamma, beta, meta, pooled, hidden_out_or_null);
+    if (head.pooled_out != nullptr || head.logits_out != nullptr)
+        return launch_pdl(final_ln_pool_kernel<true>, dim3(n_utts), dim3(256), 0, s, x, gamma, beta, meta, pooled, hidden_out_or_null, head);
+    return launch_pdl(final_ln_pool_kernel<false>, dim3(n_utts), dim3(256), 0, s, x, gamma, beta, meta, pooled, hidden_out_or_null, head);
 }
 
 int launch_row_frames(const UttMeta* meta, int n_utts, int max_slot6, int32_t* row_frame, cudaStream_t s) {
