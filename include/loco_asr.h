@@ -139,6 +139,25 @@ LOCO_API int loco_plan_text(loco_handle* h, const int32_t* n_tokens, int n_utts,
 LOCO_API int loco_encode_text(loco_handle* h, const int32_t* tokens_dev, const int32_t* n_tokens, int n_utts, float* pooled_dev,
                               float* hidden_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- classifier head as the encoder's epilogue (the consumer of the embeddings) -------------------------------
+ * Replaces IntentClassifier.forward (speech_text/intent_classifier.py:38-50) on one utterance's own frames: the pooling
+ * the classifier was built with -- method 0 "average" (:24-26), 1 "max" (:28-30), 2 "self_attention" (:32-36:
+ * alpha = softmax_t(x_t . q), sum_t alpha_t x_t) -- and classifier = Linear(768, n_classes) (:20-22), computed inside the
+ * kernel that applies the last LayerNorm, so last_hidden_state never goes to HBM for it.
+ *   q_host  f32[768]            IntentClassifier.q        (required for method 2, else may be NULL)
+ *   w_host  f32[n_classes,768]  classifier.0.weight       (NULL: pooling only)
+ *   b_host  f32[n_classes]      classifier.0.bias
+ * loco_set_head copies the HOST arrays to the device (synchronous; may be called again to replace the head).
+ * loco_set_head_outputs names where the following loco_encode / loco_encode_text calls write, until changed:
+ *   head_pooled_dev  f32[n_utts,768]        the method's pooled vector, or NULL
+ *   logits_dev       f32[n_utts,n_classes]  classifier output, or NULL        (both NULL: head off, the default)
+ * pooled_dev of the encode call stays the masked mean whatever the method. */
+#define LOCO_POOL_AVERAGE 0
+#define LOCO_POOL_MAX 1
+#define LOCO_POOL_SELF_ATTENTION 2
+LOCO_API int loco_set_head(loco_handle* h, int method, const float* q_host, const float* w_host, const float* b_host, int n_classes);
+LOCO_API int loco_set_head_outputs(loco_handle* h, float* head_pooled_dev, float* logits_dev);
+
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 LOCO_API int64_t loco_launch_count(const loco_handle* h);
 

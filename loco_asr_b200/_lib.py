@@ -49,6 +49,8 @@ SIGNATURES = {
     "loco_encode_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "loco_plan_text": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_size_t)]),
     "loco_encode_text": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "loco_set_head": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "loco_set_head_outputs": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "loco_launch_count": (C.c_int64, [_H]),
     "loco_profile_enable": (C.c_int, [_H, C.c_int]),
     "loco_profile_collect": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -81,6 +81,9 @@ struct loco_handle {
     float* txt_pe = nullptr;      // [txt_pe_rows, 768] fp32, SpeechT5ScaledPositionalEncoding table
     int txt_pe_rows = 0;
     std::vector<LayerW> layers;
+    // classifier head fused into the last kernel (loco_set_head / loco_set_head_outputs)
+    HeadArgs head;
+    bool head_set = false;
     // debug
     int gemm_impl = 2;          // 2 = tcgen05 CTA pair [default], 0 = tcgen05 single CTA, 1 = SIMT reference
     int posconv_impl = 0;
@@ -760,7 +763,7 @@ static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, f
             LAUNCH(CAT_ROWOPS, launch_layernorm(B("ffn_res"), B("x"), w.ln2_w, w.ln2_b, R6, kHidden, s), 1);
         } else {
             // last LayerNorm fused with the masked mean-pool (+ optional compact fp32 last_hidden_state)
-            LAUNCH(CAT_ROWOPS, launch_final_ln_pool(B("ffn_res"), w.ln2_w, w.ln2_b, meta, n_utts, pooled_dev, hidden_dev, s), 1);
+            LAUNCH(CAT_ROWOPS, launch_final_ln_pool(B("ffn_res"), w.ln2_w, w.ln2_b, meta, n_utts, pooled_dev, hidden_dev, h->head, s), 1);
             break;
         }
     }
@@ -975,6 +978,41 @@ int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_t* launch
     h->prof.clear();
     h->ev_used = 0;
     h->prof_last_end = nullptr;
+    return LOCO_OK;
+}
+
+int loco_set_head(loco_handle* h, int method, const float* q_host, const float* w_host, const float* b_host, int n_classes) {
+    if (!h) return LOCO_ERR_INVALID;
+    if (method < kPoolAverage || method > kPoolAttention) return fail(h, LOCO_ERR_INVALID, "loco_set_head: method must be 0 (average), 1 (max) or 2 (self_attention)");
+    if (method == kPoolAttention && !q_host) return fail(h, LOCO_ERR_INVALID, "loco_set_head: self_attention pooling needs q");
+    if ((w_host == nullptr) != (b_host == nullptr) || (w_host && n_classes <= 0) || n_classes < 0)
+        return fail(h, LOCO_ERR_INVALID, "loco_set_head: classifier weight, bias and n_classes go together");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());     // an encode in flight may still read the previous head
+    HeadArgs a;
+    a.method = method;
+    a.n_classes = w_host ? n_classes : 0;
+    int rc;
+    if (q_host) {
+        std::vector<float> q(q_host, q_host + kHidden);
+        if ((rc = upload(h, q, const_cast<float**>(&a.q)))) return rc;
+    }
+    if (w_host) {
+        std::vector<float> w(w_host, w_host + (size_t)n_classes * kHidden), b(b_host, b_host + n_classes);
+        if ((rc = upload(h, w, const_cast<float**>(&a.w)))) return rc;
+        if ((rc = upload(h, b, const_cast<float**>(&a.b)))) return rc;
+    }
+    h->head = a;
+    h->head_set = true;
+    return LOCO_OK;
+}
+
+int loco_set_head_outputs(loco_handle* h, float* head_pooled_dev, float* logits_dev) {
+    if (!h) return LOCO_ERR_INVALID;
+    if ((head_pooled_dev || logits_dev) && !h->head_set) return fail(h, LOCO_ERR_STATE, "loco_set_head_outputs before loco_set_head");
+    if (logits_dev && !h->head.w) return fail(h, LOCO_ERR_STATE, "loco_set_head_outputs: logits requested but the head has no classifier weights");
+    h->head.pooled_out = head_pooled_dev;
+    h->head.logits_out = logits_dev;
     return LOCO_OK;
 }
 

@@ -165,10 +165,58 @@ class LocoSpeechT5Encoder:
         return self._workspace[off:]
 
     # ------------------------------------------------------------------ var-len fast path (device buffers)
+    # ------------------------------------------------------------------ classifier head as the encoder's epilogue
+    _POOL_METHODS = {"average": 0, "max": 1, "attention": 2, "self_attention": 2}
+
+    def set_head(self, head=None, method: Optional[str] = None, q=None, weight=None, bias=None):
+        """Fuse the intent classifier (``speech_text/intent_classifier.py:14-50``) into the last encoder kernel.
+        ``head`` is a ``loco_asr_b200.head.IntentHead`` (or pass method / q [1,768] / weight [C,768] / bias [C]).  Afterwards
+        ``encode_packed(..., with_head=True)`` / ``encode_text_packed(..., with_head=True)`` also return the method's pooled
+        vector and the logits."""
+        if head is not None:
+            method, q, weight, bias = head.method, head.q, head.weight, head.bias
+        if method not in self._POOL_METHODS:
+            raise ValueError(f"unknown pooling method {method!r} (reference: average / max / self_attention)")
+
+        def host(t, n):
+            if t is None:
+                return None
+            a = np.ascontiguousarray(torch.as_tensor(t).detach().to("cpu", torch.float32).reshape(-1).numpy())
+            if a.size != n:
+                raise _lib.LocoError(f"head tensor has {a.size} elements, expected {n}")
+            return a
+
+        hid = self.config.hidden_size
+        n_classes = int(weight.shape[0]) if weight is not None else 0
+        qh, wh, bh = host(q, hid), host(weight, n_classes * hid), host(bias, n_classes)
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        with torch.cuda.device(self.device):
+            rc = self._lib.loco_set_head(self._h, self._POOL_METHODS[method], ptr(qh), ptr(wh), ptr(bh), n_classes)
+        _lib.check(self._lib, self._h, rc, "loco_set_head")
+        self._head_classes = n_classes
+        self._head_method = method
+
+    def _head_outputs(self, n: int, with_head: bool):
+        """Allocate the head's outputs for one encode call and point the library at them (or switch the head off)."""
+        if not with_head:
+            if getattr(self, "_head_on", False):
+                _lib.check(self._lib, self._h, self._lib.loco_set_head_outputs(self._h, None, None), "loco_set_head_outputs")
+                self._head_on = False
+            return None, None
+        if getattr(self, "_head_method", None) is None:
+            raise _lib.LocoError("with_head=True before set_head()")
+        hp = torch.empty(n, self.config.hidden_size, dtype=torch.float32, device=self.device)
+        lg = torch.empty(n, self._head_classes, dtype=torch.float32, device=self.device) if self._head_classes else None
+        rc = self._lib.loco_set_head_outputs(self._h, hp.data_ptr(), lg.data_ptr() if lg is not None else None)
+        _lib.check(self._lib, self._h, rc, "loco_set_head_outputs")
+        self._head_on = True
+        return hp, lg
+
     def encode_packed(self, wave: torch.Tensor, n_samples: Sequence[int], return_hidden: bool = False,
-                      out: Optional[torch.Tensor] = None):
+                      out: Optional[torch.Tensor] = None, with_head: bool = False):
         """wave: f32[sum(n_samples)] on this device, utterances concatenated without padding.
         Returns pooled f32[B, 768] (and the compact last_hidden_state f32[sum T, 768] if asked).
+        ``with_head=True`` (after ``set_head``): returns ``(pooled, head_pooled f32[B,768], logits f32[B,C] or None)``.
         Asynchronous on the current stream."""
         self.finalize()
         if wave.device != self.device or wave.dtype != torch.float32 or not wave.is_contiguous():
@@ -181,6 +229,7 @@ class LocoSpeechT5Encoder:
         ws = self._get_workspace(info["workspace_bytes"])
         pooled = out if out is not None else torch.empty(n, self.config.hidden_size, dtype=torch.float32, device=self.device)
         hidden = torch.empty(info["total_frames"], self.config.hidden_size, dtype=torch.float32, device=self.device) if return_hidden else None
+        head_pooled, logits = self._head_outputs(n, with_head)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             rc = self._lib.loco_encode(self._h, wave.data_ptr(), ns.ctypes.data, n, pooled.data_ptr(),
@@ -188,6 +237,11 @@ class LocoSpeechT5Encoder:
                                        ws.numel(), C.c_void_p(stream))
         _lib.check(self._lib, self._h, rc, "loco_encode")
         self._last_plan = info
+        if with_head:
+            info = dict(info, head_pooled=head_pooled, logits=logits)
+            if return_hidden:
+                return pooled, hidden, info
+            return pooled, head_pooled, logits
         if return_hidden:
             return pooled, hidden, info
         return pooled
@@ -265,9 +319,10 @@ class LocoSpeechT5Encoder:
             yield out
 
     # ------------------------------------------------------------------ text modality (reference :79-93)
-    def encode_text_packed(self, tokens: torch.Tensor, n_tokens: Sequence[int], return_hidden: bool = False):
+    def encode_text_packed(self, tokens: torch.Tensor, n_tokens: Sequence[int], return_hidden: bool = False, with_head: bool = False):
         """tokens: int32[sum(n_tokens)] on this device, texts concatenated without padding.  Each text is encoded alone.
-        Returns pooled f32[B, 768] (and the compact last_hidden_state f32[sum n_tokens, 768] if asked)."""
+        Returns pooled f32[B, 768] (and the compact last_hidden_state f32[sum n_tokens, 768] if asked); ``with_head`` as in
+        ``encode_packed``."""
         self.finalize()
         if tokens.device != self.device or tokens.dtype != torch.int32 or not tokens.is_contiguous():
             raise _lib.LocoError("encode_text_packed wants a contiguous int32 token tensor on " + str(self.device))
@@ -282,6 +337,7 @@ class LocoSpeechT5Encoder:
         ws = self._get_workspace(int(wsb.value))
         pooled = torch.empty(n, self.config.hidden_size, dtype=torch.float32, device=self.device)
         hidden = torch.empty(int(total.value), self.config.hidden_size, dtype=torch.float32, device=self.device) if return_hidden else None
+        head_pooled, logits = self._head_outputs(n, with_head)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             rc = self._lib.loco_encode_text(self._h, tokens.data_ptr(), nt.ctypes.data, n, pooled.data_ptr(),
@@ -290,6 +346,11 @@ class LocoSpeechT5Encoder:
         _lib.check(self._lib, self._h, rc, "loco_encode_text")
         info = {"frames": nt.copy(), "rows": rows, "total_frames": int(total.value), "workspace_bytes": int(wsb.value)}
         self._last_plan = info
+        if with_head:
+            info = dict(info, head_pooled=head_pooled, logits=logits)
+            if return_hidden:
+                return pooled, hidden, info
+            return pooled, head_pooled, logits
         if return_hidden:
             return pooled, hidden, info
         return pooled

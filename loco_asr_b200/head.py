@@ -5,7 +5,9 @@ The reference pools over ``pad_sequence``-zero-padded [B, T_max, 768] batches wi
 (``train_classifier.py:47-51``, ``intent_classifier.py:24-36``); on an unpadded sequence the two agree, which is
 the case this module computes (each utterance over its own frames).  The masked mean is what the encoder's
 ``pooled`` output already is (fused into the last LayerNorm, csrc/rowops.cu), so ``average`` is just the Linear.
-Plain torch: 155 kFLOP per utterance, not a kernel-worthy stage.
+This class is the plain-torch form (used on stored embeddings and as the tests' restatement of the reference forward);
+``LocoSpeechT5Encoder.set_head(head)`` + ``encode_packed(..., with_head=True)`` runs the same pooling + Linear inside the
+encoder's last kernel (csrc/rowops.cu ``final_ln_pool_kernel<true>``), so the [T, 768] sequence never leaves the GPU.
 """
 from __future__ import annotations
 

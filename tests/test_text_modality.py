@@ -78,6 +78,28 @@ def test_text_path_matches_golden_and_oracle(text_encoder, tsd):
 
 
 @pytest.mark.gpu
+def test_text_path_with_fused_classifier_head(text_encoder):
+    """-m text embeddings feed the same IntentClassifier (train_classifier.py); the fused head serves both modalities."""
+    from loco_asr_b200.head import IntentHead
+    from loco_asr_b200.synth import synth_head
+    w, b = synth_head(11)
+    q = torch.randn(1, 768, generator=torch.Generator().manual_seed(11)) * 0.08
+    toks = text_tokens(0)
+    packed = torch.from_numpy(np.concatenate(toks)).to(torch.int32).cuda()
+    for method in ("average", "max", "attention"):
+        head = IntentHead(w, b, q, method)
+        text_encoder.set_head(head)
+        pooled, hidden, info = text_encoder.encode_text_packed(packed, [len(t) for t in toks], return_hidden=True, with_head=True)
+        torch.cuda.synchronize()
+        want_p = head.pool(hidden.cpu(), info["frames"].tolist())
+        want_l = head.logits(want_p)
+        got_p, got_l = info["head_pooled"].cpu(), info["logits"].cpu()
+        assert torch.allclose(got_p, want_p, rtol=0, atol=2e-5 * float(want_p.abs().max())), method
+        assert torch.allclose(got_l, want_l, rtol=0, atol=1e-4 * max(1.0, float(want_l.abs().max()))), method
+        assert torch.equal(got_l.argmax(dim=1), want_l.argmax(dim=1))
+
+
+@pytest.mark.gpu
 def test_text_call_surface_and_errors(text_encoder, tsd):
     """encoder(input_ids) as the reference calls it (no mask: every position is a token), with a mask, and the errors."""
     from loco_asr_b200._lib import LocoError
