@@ -65,11 +65,29 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2*>(&rd);
 }
-// gelu_erf on a pair with the packed FP32 pipe (FMUL2 / FFMA2 / FADD2): 6 issue slots per element instead of 11
+// gelu_erf on a pair with the packed FP32 pipe (FMUL2 / FFMA2 / FADD2).
+// LOCO_GELU_TANH (default): the same odd quintic u(v), evaluated as 0.5 v (1 + tanh(u)) with ONE MUFU op per element
+// (tanh.approx.f32, |abs err| < 5e-4 on tanh -> < 2.5e-4 |v| on the result, below the bf16 rounding of the stored
+// activation) instead of ex2 + rcp: conv0's epilogue sat at the MUFU limit of 16 results / clk / SM (frontend 2.03 -> 1.71 ms
+// per step; the GEMM epilogues are hidden under the next tile's MMAs and did not change).
+#ifndef LOCO_GELU_TANH
+#define LOCO_GELU_TANH 1
+#endif
 __device__ __forceinline__ float2 gelu_erf2(float2 v) {
     float2 v2 = mul_f32x2(v, v);
     v2.x = fminf(v2.x, 64.0f);
     v2.y = fminf(v2.y, 64.0f);
+#if LOCO_GELU_TANH
+    // u = -(v t) / (2 log2 e), constants of gelu_erf scaled by -0.34657359027997264
+    float2 t = fma_f32x2(v2, make_float2(-0.00035151679f, -0.00035151679f), make_float2(0.037005646f, 0.037005646f));
+    t = fma_f32x2(v2, t, make_float2(0.79750788f, 0.79750788f));
+    const float2 u = mul_f32x2(v, t);
+    float2 th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(u.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(u.y));
+    const float2 h = mul_f32x2(v, make_float2(0.5f, 0.5f));
+    return fma_f32x2(h, th, h);
+#else
     float2 t = fma_f32x2(v2, make_float2(0.0010142630552579922f, 0.0010142630552579922f),
                          make_float2(-0.10677572400266595f, -0.10677572400266595f));
     t = fma_f32x2(v2, t, make_float2(-2.3011213394570755f, -2.3011213394570755f));
@@ -79,6 +97,7 @@ __device__ __forceinline__ float2 gelu_erf2(float2 v) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
     return mul_f32x2(v, r);
+#endif
 }
 __device__ __forceinline__ float add_f32_f16(float a, unsigned short h) {
     float r;

@@ -104,3 +104,14 @@ def test_gelu_sigmoid_quintic_error_bound():
     assert np.abs(g - ref).max() < 3e-5
     big = np.abs(ref) > 0.05
     assert (np.abs(g - ref)[big] / np.abs(ref[big])).max() < 5e-4        # 8x below one bf16 ulp (2^-8)
+    # gelu_erf2 (the packed epilogue form): the same quintic with its constants scaled by -1 / (2 log2 e), evaluated as
+    # 0.5 v (1 + tanh(u)).  With an exact tanh it is the same function; the hardware tanh.approx.f32 adds at most
+    # 2^-10.987 absolute on tanh, i.e. 2.5e-4 |v| on the result -- still under half a bf16 ulp of |v|.
+    c = np.float32(-0.34657359027997264)
+    t2 = np.float32(0.79750788) + v2 * (np.float32(0.037005646) + v2 * np.float32(-0.00035151679))
+    assert abs(float(np.float32(-2.3011213394570755) * c) - 0.79750788) < 1e-7
+    g2 = (np.float32(0.5) * v * (np.float32(1) + np.tanh((v * t2).astype(np.float64)))).astype(np.float32)
+    assert np.abs(g2 - ref).max() < 3e-5
+    worst = np.abs(g2 - ref) + 2.0 ** -10.987 * 0.5 * np.abs(v)
+    keep = np.abs(v) <= 8
+    assert (worst[keep] / np.maximum(np.abs(v[keep]), 1e-3)).max() < 2.0 ** -9          # half a bf16 ulp of |v|
