@@ -171,6 +171,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may park the thread for a hardware-defined time; test_wait returns at once): for warps that
+// poll several barriers and act on whichever completes first.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // try_wait with a suspend-time hint: a failed probe parks the warp (NANOSLEEP.SYNCS: until the barrier's phase completes or
 // `ns` nanoseconds pass) instead of returning after ~50 cycles, so a waiting warp stops competing for issue slots with the
 // warps doing the work -- it matters in the persistent kernels, whose idle roles would otherwise poll at full speed.

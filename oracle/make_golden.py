@@ -8,6 +8,10 @@ Fixtures
                    and the reference's literal batch_size=2 padded run (informational).
   text_hf.npz      text modality: 6 seeded token sequences (1..120 tokens) through the unmodified HF
                    SpeechT5EncoderWithTextPrenet, weights seed 0 + text prenet seed 0: pooled, first / last token rows.
+  config5_hf.npz   BASELINE.json configs[4] / SURVEY.md 8(d) "Config 5": a fixed 512-utterance subset (every ~137th) of the
+                   70k SLURP-shaped set (lengths seed 1234, weights seed 1, waveform seed 1234): the HF module's pooled embedding
+                   (stored fp16), and logits / argmax of IntentClassifier(average) with the seed-3 random Linear(768,101)
+                   computed from the fp32 pooled vector.   ``python -m oracle.make_golden --config5-only``
   short_taps.npz   one 0.4 s noise utterance (T=19, all taps) and one 1.3 s utterance (T=64, three taps): stage-by-stage taps of the oracle
                    restatement *after* it has been checked against the HF module to 2e-5.
 """
@@ -58,6 +62,30 @@ def make_text(out_dir):
              last_row=torch.stack([h[-1] for h in hs]).numpy().astype(np.float32), weights_seed=0)
 
 
+def config5_ids(n_total: int = 70000, n: int = 512):
+    return np.linspace(0, n_total - 1, n).astype(np.int64)
+
+
+def make_config5(out_dir):
+    from loco_asr_b200.synth import slurp_shaped_lengths, synth_head
+    lengths = slurp_shaped_lengths(70000, 1234)
+    ids = config5_ids()
+    model = build_hf_encoder(synth_state_dict(seed=1))
+    w, b = synth_head(3)
+    pooled = []
+    for k in range(0, len(ids), 16):
+        waves = [synth_wave(int(lengths[i]), 1234, int(i)) for i in ids[k:k + 16]]
+        pooled += [h.mean(0) for h in hf_encode_unpadded(model, waves)]
+        print(f"config5: {k + 16}/{len(ids)}", flush=True)
+    pooled = torch.stack(pooled)
+    logits = torch.nn.functional.linear(pooled, w, b)
+    top2 = logits.topk(2, dim=1).values
+    np.savez_compressed(os.path.join(out_dir, "config5_hf.npz"), ids=ids, n_samples=lengths[ids].astype(np.int64),
+                        pooled_f16=pooled.numpy().astype(np.float16), logits=logits.numpy().astype(np.float32),
+                        argmax=logits.argmax(dim=1).numpy().astype(np.int64),
+                        margin=(top2[:, 0] - top2[:, 1]).numpy().astype(np.float32), weights_seed=1, wave_seed=1234, head_seed=3)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -65,10 +93,15 @@ def main():
     model = build_hf_encoder(sd)
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--config5-only" in sys.argv:
+        make_config5(out_dir)
+        return
     make_text(out_dir)
     if "--text-only" in sys.argv:
         return
 
+    if "--with-config5" in sys.argv:
+        make_config5(out_dir)
     lengths = config1_lengths()
     waves = [synth_wave(n, 0, i) for i, n in enumerate(lengths)]
     hs = hf_encode_unpadded(model, waves)
