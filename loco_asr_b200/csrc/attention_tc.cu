@@ -147,7 +147,7 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity, int tag 
 // Phase timeline of CTA 0 (first 64 items), compiled in with -DLOCO_ATTN_TRACE: SM clock at fixed points of the softmax
 // warps 0 / 4 (groups 0 / 1) and of the two MMA warps; printed by launch_attention_tc when LOCO_ATTN_TRACE is set.
 #ifdef LOCO_ATTN_TRACE
-__device__ unsigned g_fa_trace[4][64][16];
+__device__ unsigned g_fa_trace[10][64][16];
 #define TR(role, item_n, k)                                                                          \
     do {                                                                                             \
         if (blockIdx.x == 0 && lane == 0 && (item_n) < 64) {                                         \
@@ -319,13 +319,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         for (int item = blockIdx.x;; item += gridDim.x, ++n) {
             const int qs = n & 1;
             const bool has_next = item + (int)gridDim.x < n_items;
-            TR(2 + g, n, 0);
+            TR(8 + g, n, 0);
             if (g == 0 && cur.nc16 > G_ROUND1) {       // second G round over the first 128 columns, once they are drained
                 bar_wait(smem_u32(&bars->g_lo_free), (uint32_t)(n & 1), 206);
                 tc_fence_after();
                 issue_g(cur, qs, 1);
             }
-            TR(2 + g, n, 1);
+            TR(8 + g, n, 1);
             const uint32_t e_next = e + (cur.n_kv > g ? (uint32_t)((cur.n_kv - g + 1) >> 1) : 0u);   // ring entry of the next item's lone K
             bool ga_seen = false;
             // The next item's prologue (G_{n+1}, this group's first S_{n+1}) is issued as soon as its inputs exist, but never
@@ -353,7 +353,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     nxt.set(descs[(n + 1) & 3]);
                     tc_fence_after();
                     if (g == 0) issue_g(nxt, qs ^ 1, 0);
-                    TR(2 + g, n, 4);
+                    TR(8 + g, n, 4);
                     nx = g < nxt.n_kv ? 2 : 3;
                 }
                 if (nx == 2) {
@@ -369,14 +369,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             for (int j = g; j < cur.n_kv; j += 2, ++e, ++n_pv) {
                 const int slot = e % NS;
                 bar_wait(kvf + slot * 8, (e / NS) & 1, 203);
-                if (j == g) TR(2 + g, n, 5);
+                if (j == g) TR(8 + g, n, 5);
                 // ---- the next S of this group goes out first: it only needs the S buffer (read early in the block) ----------
                 if (j + 2 < cur.n_kv) {
                     issue_s(cur, qs, j + 2, slot);
                     if (j + 4 >= cur.n_kv) start_next();
                 }
                 // ---- O_g += P_j V_j ---------------------------------------------------------------------------------------------
-                if (j == g) TR(2 + g, n, 6);
+                if (j == g) TR(8 + g, n, 6);
+                // (backing off between probes -- __nanosleep(64), or try_wait once nothing is left to advance -- measured slower:
+                //  0.227-0.243 -> 0.242-0.249 ms per layer at 128 frames, 0.319-0.327 -> 0.344 at 256)
                 for (uint32_t spins = 0; !ready(pfull, n_pv & 1);) {
                     if (nx == 1 || nx == 2) advance_next(false);
                     if (++spins > (1u << 20)) {
@@ -384,7 +386,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                         break;
                     }
                 }
-                if (j == g) TR(2 + g, n, 7);
+                if (j == g) TR(8 + g, n, 7);
                 tc_fence_after();
                 const uint64_t dv = umma_desc_sw128_mnmajor(ring + slot * ENTRY_B);
                 const int valid = cur.klen(j);
@@ -408,7 +410,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             }
             // o_full needs both groups' last P.V; it may only complete once every softmax thread has seen the previous
             // item's o_full (ga_empty), so a waiter is never lapped by two phases
-            TR(2 + g, n, 8);
+            TR(8 + g, n, 8);
             if (!ga_seen) {
                 bar_wait(smem_u32(&bars->ga_empty), (uint32_t)(n & 1), 207);
                 ga_seen = true;
@@ -417,7 +419,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 if (g < cur.n_kv) umma_commit(smem_u32(&bars->o_full));
                 else mbar_arrive(smem_u32(&bars->o_full));
             }
-            TR(2 + g, n, 9);
+            TR(8 + g, n, 9);
             if (!has_next) break;
             advance_next(true);
             if (g < nxt.n_kv) ++e;
@@ -452,7 +454,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         // 2-3 s utterances).
         auto epilogue = [&]() {
             bar_wait(smem_u32(&bars->o_full), (uint32_t)((n - 1) & 1), 309);
-            if (q == 0) TR(g, n, 11);
+            TR(warp, n, 11);
             tc_fence_after();
             const uint32_t stage = sbase + SM_Q + ((n - 1) & 1) * Q_TILE_B;
             if (prev_active) {
@@ -492,7 +494,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     }
                 }
                 tc_fence_before();
-                if (q == 0) TR(g, n, 12);
+                TR(warp, n, 12);
                 named_bar_sync(bar_id, 64);       // both halves of the quad's rows are staged, and both groups have read both
                                                   // accumulators before either P.V restarts them
                 // warp (q, g) writes rows 32 q + 16 g + [0, 16): 8 lanes per row, 4 full lines per instruction
@@ -505,7 +507,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     }
                 }
             }
-            if (q == 0) TR(g, n, 13);
+            TR(warp, n, 13);
             fence_proxy_async_smem();             // generic accesses to the slot are ordered before the TMA refill
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->q_empty[(n - 1) & 1]));
@@ -514,9 +516,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
             // G_n complete also means the item's descriptor is in place (the MMA warp read it before issuing G_n).  The
             // Q barriers cannot be used for that: a Q slot may be released and refilled before a softmax thread looks.
-            if (q == 0) TR(g, n, 0);
+            TR(warp, n, 0);
             bar_wait(smem_u32(&bars->g_full), (uint32_t)(n & 1), 310);
-            if (q == 0) TR(g, n, 1);
+            TR(warp, n, 1);
             tc_fence_after();
             Item it;
             it.set(descs[n & 3]);
@@ -551,25 +553,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 for (int c = G_LO_CHUNKS + g; c < min(n_chunks, G_ROUND1 / 32); c += 2) drain(c, c * 32);
 
             // ---- previous item's epilogue (its last P.V ran while the table was drained; the second G round runs now) ----
-            if (q == 0) TR(g, n, 2);
+            TR(warp, n, 2);
             if (n > 0) epilogue();
-            if (q == 0) TR(g, n, 3);
+            TR(warp, n, 3);
 
             if (it.nc16 > G_ROUND1) {
                 bar_wait(smem_u32(&bars->g2_full), n_g2 & 1, 311);
-                if (q == 0) TR(g, n, 14);
+                TR(warp, n, 14);
                 ++n_g2;
                 tc_fence_after();
                 if (active)
                     for (int c = G_ROUND1 / 32 + g; c < n_chunks; c += 2) drain(c, (c - G_ROUND1 / 32) * 32);
             }
-            if (q == 0) TR(g, n, 15);
+            TR(warp, n, 15);
             if (active) named_bar_sync(bar_id, 64);       // both column sets of my rows are in place
             // G has left TMEM -- and this thread has seen o_full of the previous item, so o_full (which the MMA warps only
             // complete for item n after this barrier) can never run two phases ahead of a waiter
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->ga_empty));
-            if (q == 0) TR(g, n, 4);
+            TR(warp, n, 4);
 
             float row_max = -INFINITY, row_sum = 0.f;
             const int iw0 = it.i0 + q * 32;            // first query row of this warp
@@ -579,7 +581,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 const int j0 = it.k0(j), jlen = it.klen(j);
                 const int nch = active ? (jlen + 31) >> 5 : 0;      // 32-key chunks that hold keys
                 bar_wait(smem_u32(&bars->s_full[g]), cnt & 1, 312);
-                if (q == 0 && j == g) TR(g, n, 5);
+                if (j == g) TR(warp, n, 5);
                 tc_fence_after();
                 uint32_t su[2][32];                // scores, fp32 bit patterns (one array from the TMEM load to the exponentials)
                 if (nch > 0) tmem_ld_32x32(t_s, su[0]);
@@ -591,7 +593,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     for (int e = 0; e < 32; ++e) asm volatile("" : "+r"(su[c][e]));
                 tc_fence_before();
                 mbar_arrive(smem_u32(&bars->s_empty[g]));     // the group's next S may be written
-                if (q == 0 && j == g) TR(g, n, 6);
+                if (j == g) TR(warp, n, 6);
 #define SC(c, e) __uint_as_float(su[c][e])
 #define SET_SC(c, e, v) su[c][e] = __float_as_uint(v)
                 float cbias[2] = {0.f, 0.f};       // per-chunk scalar bias (clamped regions), folded into the exp argument
@@ -630,12 +632,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     }
                     mloc = fmaxf(mloc, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) + cbias[c]);
                 }
-                if (q == 0 && j == g) TR(g, n, 7);
+                if (j == g) TR(warp, n, 7);
                 if (cnt > 0) {          // P_g and O_g are free once this group's previous P.V has completed (issued a block ago)
                     bar_wait(smem_u32(&bars->pv_done[g]), (cnt - 1) & 1, 314);
                     tc_fence_after();
                 }
-                if (q == 0 && j == g) TR(g, n, 8);
+                if (j == g) TR(warp, n, 8);
                 if (active && __any_sync(0xffffffffu, mloc > row_max + kLazyRescale)) {
                     const float mx = fmaxf(row_max, mloc);
                     const float corr = ex2_approx(row_max - mx);      // first block: exp2(-inf) = 0
@@ -674,12 +676,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&bars->p_full[g]));
-                if (q == 0 && j == g) TR(g, n, 9);
+                if (j == g) TR(warp, n, 9);
 #undef SC
 #undef SET_SC
             }
             // ---- partial results of this group; the epilogue is deferred behind the next item's table drain ---------------
-            if (q == 0) TR(g, n, 10);
+            TR(warp, n, 10);
             prev_active = active;
             if (active) {
                 xm[g * FQ + row] = row_max;
@@ -718,20 +720,26 @@ int launch_attention_tc(const void* qkv_map, const void* pe_map, const PcTile* t
 #ifdef LOCO_ATTN_TRACE
     static int traced = 0;
     if (!rc && getenv("LOCO_ATTN_TRACE") != nullptr && traced++ == 2) {       // third launch: caches and clocks are warm
-        static unsigned t[4][64][16];
+        static unsigned t[10][64][16];
         rc = (int)cudaStreamSynchronize(s);
         if (!rc) rc = (int)cudaMemcpyFromSymbol(t, g_fa_trace, sizeof t);
-        const char* names[4] = {"softmax g0", "softmax g1", "mma g0", "mma g1"};
-        for (int r = 0; r < 4; ++r) {
-            fprintf(stderr, "trace %s (items %d grid %d): clock relative to the role's point 0 of the item; last column = next item's point 0\n", names[r], n_items, grid);
-            for (int n = 4; n < 12; ++n) {
-                fprintf(stderr, "  item %2d:", n);
-                for (int k = 0; k < 16; ++k) fprintf(stderr, " %6d", r >= 2 && k > 9 ? 0 : (int)(t[r][n][k] - t[r][n][0]));
-                fprintf(stderr, " | %6d\n", (int)(t[r][n + 1][0] - t[r][n][0]));
+        const char* names[10] = {"softmax g0 q0", "softmax g0 q1", "softmax g0 q2", "softmax g0 q3", "softmax g1 q0", "softmax g1 q1",
+                                 "softmax g1 q2", "softmax g1 q3", "mma g0", "mma g1"};
+        const unsigned origin = t[0][6][0];
+        fprintf(stderr, "attention_tc phase trace of CTA 0, items 6..8 (items %d, grid %d); SM clocks since softmax warp 0 entered item 6\n", n_items, grid);
+        fprintf(stderr, "softmax points: 0 top, 1 g_full, 2 drained round 1, 11 o_full, 12 staged, 13 stored, 3 epilogue done, 14 g2_full, 15 drained round 2,\n"
+                        "  4 ga_empty arrived, 5 s_full, 6 S in registers, 7 bias+max, 8 pv_done, 9 P stored, 10 item end\n"
+                        "mma points: 0 top, 1 after G round 2, 4 next G issued, 5 V entry full, 6 before p_full wait, 7 p_full, 8 P.V issued, 9 o_full committed\n");
+        const int order[16] = {0, 1, 2, 11, 12, 13, 3, 14, 15, 4, 5, 6, 7, 8, 9, 10};
+        for (int r = 0; r < 10; ++r)
+            for (int n = 6; n < 9; ++n) {
+                fprintf(stderr, "%-14s item %d:", names[r], n);
+                if (r < 8)
+                    for (int k = 0; k < 16; ++k) fprintf(stderr, " %6d", (int)(t[r][n][order[k]] - origin));
+                else
+                    for (int k = 0; k < 10; ++k) fprintf(stderr, " %6d", k == 2 || k == 3 ? 0 : (int)(t[r][n][k] - origin));
+                fprintf(stderr, "\n");
             }
-            fprintf(stderr, "  absolute point 0 of items 4..7 relative to softmax g0 item 4: %d %d %d %d\n", (int)(t[r][4][0] - t[0][4][0]),
-                    (int)(t[r][5][0] - t[0][4][0]), (int)(t[r][6][0] - t[0][4][0]), (int)(t[r][7][0] - t[0][4][0]));
-        }
     }
 #endif
     static const bool debug = getenv("LOCO_ATTN_DEBUG") != nullptr;

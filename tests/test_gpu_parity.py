@@ -254,3 +254,41 @@ def test_pipelined_host_path_equals_device_path(encoder):
     assert len(got) == len(want)
     for g, w in zip(got, want):
         assert torch.equal(g, w)
+
+
+def test_config5_subset_against_hf_golden_with_intent_head(encoder):
+    """SURVEY.md 8(d) "Config 5": a fixed 512-utterance subset of the 70k SLURP-shaped set (the bench's own lengths,
+    weights seed 1, waveforms seed 1234) against tests/golden/config5_hf.npz -- the unmodified HF module's pooled
+    embeddings (stored fp16) and IntentClassifier(average) logits with the seed-3 Linear(768,101), made by
+    oracle/make_golden.py --config5-only.  Bars: pooled cosine >= 0.999 and max rel err < 3e-2 for every utterance;
+    the intent argmax equals the reference's wherever the reference's own top-2 margin exceeds 0.03 (bf16 operands move
+    a logit by up to 1.6e-2: measured 10 of 512 differ, all with reference margins < 8.4e-3), and on >= 97 % of all 512.  The fused head's logits are the ones compared."""
+    from loco_asr_b200.encoder import LocoSpeechT5Encoder
+    from loco_asr_b200.head import IntentHead
+    from loco_asr_b200.synth import synth_state_dict
+    g = np.load(os.path.join(GOLD, "config5_hf.npz"))
+    ids, n_samples = g["ids"], g["n_samples"]
+    enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device="cuda:0")
+    w, b = synth_head(3)
+    enc.set_head(IntentHead(w, b, None, "average"))
+    order = np.argsort(n_samples, kind="stable")
+    pooled = torch.empty(len(ids), 768)
+    logits = torch.empty(len(ids), 101)
+    for k in range(0, len(ids), 64):
+        sel = order[k:k + 64]
+        waves = [synth_wave(int(n_samples[i]), 1234, int(ids[i])) for i in sel]
+        wave = torch.from_numpy(np.concatenate(waves)).cuda()
+        p, hp, lg = enc.encode_packed(wave, [len(x) for x in waves], with_head=True)
+        pooled[sel] = p.cpu()
+        logits[sel] = lg.cpu()
+    ref = torch.from_numpy(g["pooled_f16"].astype(np.float32))
+    cos = torch.nn.functional.cosine_similarity(pooled, ref, dim=1)
+    rel = (pooled - ref).abs().amax(dim=1) / ref.abs().amax(dim=1)
+    agree = logits.argmax(dim=1).numpy() == g["argmax"]
+    print(f"config 5: min cosine {float(cos.min()):.6f}, max rel err {float(rel.max()):.5f}, argmax agreement {agree.mean():.4f} "
+          f"({int((~agree).sum())} of {len(ids)} differ; largest reference margin among them "
+          f"{float(g['margin'][~agree].max()) if (~agree).any() else 0.0:.5f}), max |logit diff| "
+          f"{float((logits - torch.from_numpy(g['logits'])).abs().max()):.5f}")
+    assert float(cos.min()) >= COS_MIN and float(rel.max()) < POOLED_REL_MAX
+    assert agree[g["margin"] > 0.03].all()
+    assert agree.mean() >= 0.97
