@@ -41,7 +41,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", choices=["loco", "reference"], default="loco")
     p.add_argument("--utts", type=int, default=70000)
-    p.add_argument("--max-frames", type=int, default=65536)
+    p.add_argument("--max-frames", type=int, default=131072)
     p.add_argument("--e2e-steps", type=int, default=16)
     p.add_argument("--cpu-sample", type=int, default=96, help="utterances in the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -346,7 +346,7 @@ def main():
                        "utterances_per_gpu": int(args.utts), "batches": nb,
                        "max_frames_per_batch": args.max_frames, "audio_s_per_step": timed_audio / K / max(world, 1),
                        "weights": "random-init SpeechT5-base (seed 1)", "accumulate": "fp32",
-                       "l2": "inputs larger than L2 (per-step working set ~10 GB)",
+                       "l2": "inputs larger than L2 (per-step working set ~20 GB)",
                        "parallelism": f"dp{world} utterance-sharded, one all-gather of pooled embeddings"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "stage_ms_per_step": stage_ms, "whole_step": whole, "parity": parity,

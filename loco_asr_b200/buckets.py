@@ -24,7 +24,7 @@ def frames_of(lengths: Sequence[int], cfg: LocoSpeechT5Config | None = None) -> 
     return t
 
 
-def make_batches(lengths: Sequence[int], max_frames: int = 65536, max_utts: int = 32768,
+def make_batches(lengths: Sequence[int], max_frames: int = 131072, max_utts: int = 32768,
                  cfg: LocoSpeechT5Config | None = None) -> List[np.ndarray]:
     """Sort by length and cut into batches of at most `max_frames` encoder frames (+2 slot rows per utterance).
     Returns index arrays into `lengths`; every utterance appears exactly once."""

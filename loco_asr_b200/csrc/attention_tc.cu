@@ -638,7 +638,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     tc_fence_after();
                 }
                 if (j == g) TR(warp, n, 8);
-                if (active && __any_sync(0xffffffffu, mloc > row_max + kLazyRescale)) {
+                // (only rows that exist vote: the lanes past the utterance's last query hold a neighbour's rows, and letting them
+                //  trigger a rescale made the valid rows' rounding depend on the batch the utterance travelled in)
+                if (active && __any_sync(0xffffffffu, row < it.nr && mloc > row_max + kLazyRescale)) {
                     const float mx = fmaxf(row_max, mloc);
                     const float corr = ex2_approx(row_max - mx);      // first block: exp2(-inf) = 0
                     row_max = mx;

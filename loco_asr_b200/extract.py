@@ -145,7 +145,7 @@ def write_item(folder: str, slurp_id, embedding: np.ndarray, target: np.ndarray)
 
 
 # ------------------------------------------------------------------------------------------------ main
-def run(encoder, items, waves_fn, binarize, folder: str, full_sequence: bool = False, max_frames: int = 65536,
+def run(encoder, items, waves_fn, binarize, folder: str, full_sequence: bool = False, max_frames: int = 131072,
         writers: int = 8, resume: bool = True, log=print):
     """items: [(slurp_id, key, intent)]; waves_fn(key) -> float32 waveform."""
     import torch
@@ -207,7 +207,7 @@ def load_tokenizer(name_or_path: str):
     return lambda sentence: np.asarray(tok(sentence)["input_ids"], dtype=np.int64)
 
 
-def run_text(encoder, items, tokens_fn, binarize, folder: str, full_sequence: bool = False, max_tokens: int = 65536,
+def run_text(encoder, items, tokens_fn, binarize, folder: str, full_sequence: bool = False, max_tokens: int = 131072,
              writers: int = 8, resume: bool = True, log=print):
     """Text modality: items [(slurp_id, sentence-key, intent)]; tokens_fn(key) -> int token ids.  Same files as run()."""
     import torch
@@ -267,7 +267,7 @@ def main(argv=None):
     p.add_argument("--full-sequence", action="store_true", help="write [T, 768] like the reference instead of pooled [1, 768]")
     p.add_argument("--synthetic", type=int, default=0, help="use N synthetic SLURP-shaped utterances and random-init weights")
     p.add_argument("--device", default="cuda:0")
-    p.add_argument("--max-frames", type=int, default=65536)
+    p.add_argument("--max-frames", type=int, default=131072)
     p.add_argument("--do-normalize", action="store_true", help="zero-mean / unit-variance waveforms (the feature extractor's do_normalize)")
     p.add_argument("--tokenizer", default="microsoft/speecht5_asr", help="text modality: SpeechT5 tokenizer name or local directory")
     a = p.parse_args(argv)

@@ -292,3 +292,29 @@ def test_config5_subset_against_hf_golden_with_intent_head(encoder):
     assert float(cos.min()) >= COS_MIN and float(rel.max()) < POOLED_REL_MAX
     assert agree[g["margin"] > 0.03].all()
     assert agree.mean() >= 0.97
+
+
+@pytest.mark.parametrize("max_frames", [131072, 196608])
+def test_full_size_batch_is_bit_identical_to_single_utterance_encodes(encoder, max_frames):
+    """At the bench's batch size (131072 frames; conv0's activation is 8.6 GB, element indices pass 2^32) and beyond:
+    utterances picked from the front, the middle and the very end of one packed launch come out bit-identical to
+    encoding them alone -- the size-independent form of parity (offset arithmetic, TMA coordinates, work lists, and no
+    warp-wide decision that looks at a neighbour's rows: the lazy softmax rescale once did)."""
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    rng = np.random.default_rng(77)
+    lengths, frames = [], 0
+    while True:
+        n = int(rng.integers(16000, 160001))
+        t = (n - 400) // 320 + 1
+        if frames + t + 2 > max_frames:
+            break
+        lengths.append(n)
+        frames += t + 2
+    wave = torch.randn(int(np.sum(lengths)), device="cuda", generator=gen) * 0.1
+    pooled = encoder.encode_packed(wave, lengths)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(pooled).all())
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    for u in sorted(set(np.linspace(0, len(lengths) - 1, 12).astype(int).tolist()) | {1, len(lengths) - 2}):
+        alone = encoder.encode_packed(wave[int(offs[u]):int(offs[u + 1])].contiguous(), [lengths[u]])
+        assert torch.equal(alone[0], pooled[u]), u
