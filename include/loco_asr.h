@@ -147,7 +147,8 @@ LOCO_API int loco_encode_text(loco_handle* h, const int32_t* tokens_dev, const i
  *   q_host  f32[768]            IntentClassifier.q        (required for method 2, else may be NULL)
  *   w_host  f32[n_classes,768]  classifier.0.weight       (NULL: pooling only)
  *   b_host  f32[n_classes]      classifier.0.bias
- * loco_set_head copies the HOST arrays to the device (synchronous; may be called again to replace the head).
+ * loco_set_head copies the HOST arrays to the device (synchronous; may be called again to replace the head, which also
+ * clears the output pointers).
  * loco_set_head_outputs names where the following loco_encode / loco_encode_text calls write, until changed:
  *   head_pooled_dev  f32[n_utts,768]        the method's pooled vector, or NULL
  *   logits_dev       f32[n_utts,n_classes]  classifier output, or NULL        (both NULL: head off, the default)

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -1001,6 +1002,13 @@ int loco_set_head(loco_handle* h, int method, const float* q_host, const float* 
         std::vector<float> w(w_host, w_host + (size_t)n_classes * kHidden), b(b_host, b_host + n_classes);
         if ((rc = upload(h, w, const_cast<float**>(&a.w)))) return rc;
         if ((rc = upload(h, b, const_cast<float**>(&a.b)))) return rc;
+    }
+    // release the previous head's arrays (the device is idle: synchronised above)
+    for (const float* old : {h->head.q, h->head.w, h->head.b}) {
+        if (!old) continue;
+        auto it = std::find(h->allocs.begin(), h->allocs.end(), (void*)old);
+        if (it != h->allocs.end()) h->allocs.erase(it);
+        cudaFree((void*)old);
     }
     h->head = a;
     h->head_set = true;
