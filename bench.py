@@ -48,6 +48,7 @@ def parse_args():
     p.add_argument("--seed", type=int, default=1234)
     p.add_argument("--no-stage-events", action="store_true", help="debug: time the steps without the per-launch CUDA events (no roofline)")
     p.add_argument("--gemm-impl", type=int, default=-1, help="debug: force GEMM kernel (0 single-CTA tcgen05, 2 CTA-pair tcgen05)")
+    p.add_argument("--ln-impl", type=int, default=-1, help="debug: 0 deferred LayerNorm in the GEMM epilogues, 1 LayerNorm kernels")
     p.add_argument("--attn-impl", type=int, default=-1, help="debug: force attention kernel (0 tcgen05, 1 mma.sync)")
     p.add_argument("--workload", choices=["slurp", "long30", "long60"], default="slurp",
                    help="slurp = BASELINE configs[1] (the metric's workload); long30/long60 = configs[3] (256 x 30 s / 128 x 60 s)")
@@ -179,6 +180,8 @@ def main():
         enc.debug_set("attn_impl", args.attn_impl)
     if args.gemm_impl >= 0:
         enc.debug_set("gemm_impl", args.gemm_impl)
+    if args.ln_impl >= 0:
+        enc.debug_set("ln_impl", args.ln_impl)
     if args.workload == "slurp":
         lengths = slurp_shaped_lengths(args.utts, args.seed + rank)      # every rank owns a full set (weak scaling)
     else:

@@ -29,6 +29,10 @@ struct HostTensor {
 struct LayerW {
     bf16 *wqkv, *wo, *w1, *w2;
     float *bqkv, *bo, *b1, *b2, *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+    // deferred LayerNorm (GemmEpilogue EPI_LN_*): weights with the preceding LayerNorm's gamma folded in, their column sums
+    // c1[n] = sum_k W'[n, k] (of the bf16-rounded W', so the mean term cancels exactly) and c2[n] = sum_k beta[k] W[n, k] + b[n]
+    bf16 *wqkv_ln = nullptr, *w1_ln = nullptr;       // wqkv_ln: layers >= 1 (final_layer_norm of the layer before)
+    float *qkv_c1 = nullptr, *qkv_c2 = nullptr, *ffn_c1 = nullptr, *ffn_c2 = nullptr;
 };
 
 struct Buf {
@@ -44,6 +48,7 @@ struct Layout {
     std::vector<UttMeta> meta;
     std::vector<PcTile> pc_tiles;
     size_t off_pctiles = 0;
+    size_t off_stats1 = 0, off_stats2 = 0;      // deferred LayerNorm: row statistics of attn_res / ffn_res, [R6, 6, 2] fp32
     size_t off_at_tiles = 0, off_at_utts = 0;   // attention work lists: tcgen05 tiles / mma.sync utterance indices
     size_t off_meta = 0, off_partial = 0, off_scale = 0, off_shift = 0, off_rowframe = 0;
     std::map<std::string, Buf> bufs;
@@ -88,6 +93,7 @@ struct loco_handle {
     // debug
     int gemm_impl = 2;          // 2 = tcgen05 CTA pair [default], 0 = tcgen05 single CTA, 1 = SIMT reference
     int posconv_impl = 0;
+    int ln_impl = 0;            // 0 = LayerNorms of the transformer layers deferred into the GEMM epilogues [default], 1 = LayerNorm kernels
     int attn_impl = -1;         // -1 = by length (tcgen05 from attn_tc_min_frames), 0 = tcgen05, 1 = mma.sync
     int attn_tc_min_frames = 193;   // utterances with at least this many frames use the tcgen05 attention kernel,
     int attn_tc_lo = 84, attn_tc_hi = 128;   // ... and so do utterances that fill most of one 128-query tile (see loco_encode)
@@ -286,6 +292,8 @@ int make_layout_text(loco_handle* h, const int32_t* n_tokens, int n_utts, Layout
     L->off_meta = take((size_t)n_utts * sizeof(UttMeta));
     L->off_at_tiles = take(L->pc_tiles.size() * sizeof(PcTile));
     L->off_at_utts = take((size_t)n_utts * sizeof(int32_t));
+    L->off_stats1 = take((size_t)L->R6 * 2 * kStatSlots * sizeof(float));
+    L->off_stats2 = take((size_t)L->R6 * 2 * kStatSlots * sizeof(float));
     L->off_rowframe = take((size_t)L->R6 * sizeof(int32_t));
     auto add = [&](const char* name, int64_t rows, int64_t cols) {
         Buf b;
@@ -360,6 +368,8 @@ int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L)
     L->off_partial = take((size_t)n_utts * L->chunks * 65 * sizeof(double));
     L->off_scale = take((size_t)n_utts * kConvDim * sizeof(float));
     L->off_shift = take((size_t)n_utts * kConvDim * sizeof(float));
+    L->off_stats1 = take((size_t)L->R6 * 2 * kStatSlots * sizeof(float));
+    L->off_stats2 = take((size_t)L->R6 * 2 * kStatSlots * sizeof(float));
     L->off_rowframe = take((size_t)L->R6 * sizeof(int32_t));
     auto add = [&](const char* name, int64_t rows, int64_t cols, int64_t pad_rows) {
         Buf b;
@@ -687,6 +697,53 @@ int loco_finalize_weights(loco_handle* h) {
         if ((rc = upload_f32(h, p + "feed_forward.output_dense.bias", {768}, &w.b2))) return rc;
         if ((rc = upload_f32(h, p + "final_layer_norm.weight", {768}, &w.ln2_w))) return rc;
         if ((rc = upload_f32(h, p + "final_layer_norm.bias", {768}, &w.ln2_b))) return rc;
+        // ---- deferred LayerNorm operands: W' = gamma (.) W in bf16, c1 = row sums of W', c2 = W beta + b -----------------
+        auto fold = [&](const float* W, const float* b, const float* gamma, const float* beta, int N, float w_scale_rows_lt, int n_scaled,
+                        bf16** w_out, float** c1_out, float** c2_out) -> int {
+            std::vector<bf16> wf((size_t)N * 768);
+            std::vector<float> c1(N), c2(N);
+            for (int n = 0; n < N; ++n) {
+                const float sc = n < n_scaled ? w_scale_rows_lt : 1.0f;
+                double s1 = 0.0, s2 = 0.0;
+                for (int k = 0; k < 768; ++k) {
+                    const float wv = W[(size_t)n * 768 + k] * sc;
+                    const bf16 r = to_bf16_host(wv * gamma[k]);
+                    wf[(size_t)n * 768 + k] = r;
+                    s1 += (double)__bfloat162float(r);
+                    s2 += (double)wv * (double)beta[k];
+                }
+                c1[n] = (float)s1;
+                c2[n] = (float)(s2 + (double)b[n] * sc);
+            }
+            int rc2;
+            if ((rc2 = upload(h, wf, w_out))) return rc2;
+            if ((rc2 = upload(h, c1, c1_out))) return rc2;
+            return upload(h, c2, c2_out);
+        };
+        {
+            const HostTensor *w1t, *b1t, *g1, *be1;
+            if ((rc = get(h, p + "feed_forward.intermediate_dense.weight", {3072, 768}, &w1t))) return rc;
+            if ((rc = get(h, p + "feed_forward.intermediate_dense.bias", {3072}, &b1t))) return rc;
+            if ((rc = get(h, p + "layer_norm.weight", {768}, &g1))) return rc;
+            if ((rc = get(h, p + "layer_norm.bias", {768}, &be1))) return rc;
+            if ((rc = fold(w1t->data.data(), b1t->data.data(), g1->data.data(), be1->data.data(), 3072, 1.0f, 0, &w.w1_ln, &w.ffn_c1, &w.ffn_c2)))
+                return rc;
+        }
+        if (l > 0) {
+            const std::string pp = "wrapped_encoder.layers." + std::to_string(l - 1) + ".";
+            const HostTensor *g2, *be2;
+            if ((rc = get(h, pp + "final_layer_norm.weight", {768}, &g2))) return rc;
+            if ((rc = get(h, pp + "final_layer_norm.bias", {768}, &be2))) return rc;
+            std::vector<float> wcat((size_t)2304 * 768), bcat(2304);
+            memcpy(wcat.data(), q->data.data(), (size_t)768 * 768 * sizeof(float));
+            memcpy(wcat.data() + (size_t)768 * 768, k->data.data(), (size_t)768 * 768 * sizeof(float));
+            memcpy(wcat.data() + (size_t)2 * 768 * 768, v->data.data(), (size_t)768 * 768 * sizeof(float));
+            memcpy(bcat.data(), bq->data.data(), 768 * sizeof(float));
+            memcpy(bcat.data() + 768, bk->data.data(), 768 * sizeof(float));
+            memcpy(bcat.data() + 1536, bv->data.data(), 768 * sizeof(float));
+            if ((rc = fold(wcat.data(), bcat.data(), g2->data.data(), be2->data.data(), 2304, kQScale, 768, &w.wqkv_ln, &w.qkv_c1, &w.qkv_c2)))
+                return rc;
+        }
     }
     if (h->has_speech && (rc = build_sin_table(h, h->cfg.max_speech_positions + h->cfg.pad_token_id + 3))) return rc;
     h->host.clear();
@@ -735,12 +792,26 @@ static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, f
         return fail(h, LOCO_ERR_CUDA, "cuTensorMapEncodeTiled failed for qkv");
 
     // ---- transformer layers (post-LN) -------------------------------------------------------------------
+    // ln_impl 0 (default): no LayerNorm kernel inside the stack.  out_proj / FFN2 write the un-normalised sums u1 = x + attn(x)
+    // ("attn_res") and u2 = x' + ffn(x') ("ffn_res") together with per-row statistics; FFN1 and the next layer's QKV consume them
+    // through gamma-folded weights (EPI_LN_*), and the residual reads normalise on the fly (EPI_BIAS_LNRESIDUAL_STATS).  The last
+    // layer's u2 goes to final_ln_pool, which has always normalised it itself.  ln_impl 1 keeps the LayerNorm kernels (tests).
     const int n_layers = (int)h->layers.size();
+    const bool defer = h->ln_impl == 0 && h->gemm_impl == 2;
+    float* stats1 = reinterpret_cast<float*>(ws + L.off_stats1);
+    float* stats2 = reinterpret_cast<float*>(ws + L.off_stats2);
     for (int l = 0; l < n_layers; ++l) {
         const LayerW& w = h->layers[l];
+        const bool ln_in = defer && l > 0;         // this layer's input is the previous layer's un-normalised ffn_res
+        const LayerW& wp = h->layers[l > 0 ? l - 1 : 0];
         GemmArgs g = {};
-        g.A = B("x"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wqkv; g.C = B("qkv"); g.ldc = 3 * kHidden;
-        g.bias = w.bqkv; g.M = R6; g.N = 3 * kHidden; g.K = kHidden; g.epilogue = EPI_BIAS;
+        g.A = ln_in ? B("ffn_res") : B("x"); g.lda = kHidden; g.a_rows_alloc = R6; g.C = B("qkv"); g.ldc = 3 * kHidden;
+        g.M = R6; g.N = 3 * kHidden; g.K = kHidden;
+        if (ln_in) {
+            g.W = w.wqkv_ln; g.bias = w.qkv_c2; g.c1 = w.qkv_c1; g.stats_in = stats2; g.epilogue = EPI_LN_BIAS;
+        } else {
+            g.W = w.wqkv; g.bias = w.bqkv; g.epilogue = EPI_BIAS;
+        }
         if ((rc = run_gemm(h, g, s))) return rc;
         if (!at_utts.empty())
             LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, at_utts_dev, (int)at_utts.size(), at_ms_max_t6, B("ctx"), s), 1);
@@ -748,20 +819,36 @@ static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, f
             LAUNCH(CAT_ATTENTION, launch_attention_tc(&qkv_map, &h->pe_map, at_tiles_dev, (int)at_tiles.size(), B("ctx"), h->num_sms, s), 1);
         g = GemmArgs();
         g.A = B("ctx"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wo; g.C = B("attn_res"); g.ldc = kHidden;
-        g.bias = w.bo; g.R = B("x"); g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kHidden; g.epilogue = EPI_BIAS_RESIDUAL;
+        g.bias = w.bo; g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kHidden;
+        if (ln_in) {
+            g.R = B("ffn_res"); g.stats_in = stats2; g.ln_gamma = wp.ln2_w; g.ln_beta = wp.ln2_b; g.stats_out = stats1;
+            g.epilogue = EPI_BIAS_LNRESIDUAL_STATS;
+        } else {
+            g.R = B("x"); g.stats_out = stats1; g.epilogue = defer ? EPI_BIAS_RESIDUAL_STATS : EPI_BIAS_RESIDUAL;
+        }
         if ((rc = run_gemm(h, g, s))) return rc;
-        LAUNCH(CAT_ROWOPS, launch_layernorm(B("attn_res"), B("ln1"), w.ln1_w, w.ln1_b, R6, kHidden, s), 1);
+        if (!defer) LAUNCH(CAT_ROWOPS, launch_layernorm(B("attn_res"), B("ln1"), w.ln1_w, w.ln1_b, R6, kHidden, s), 1);
         g = GemmArgs();
-        g.A = B("ln1"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.w1; g.C = B("mid"); g.ldc = kFfn;
-        g.bias = w.b1; g.M = R6; g.N = kFfn; g.K = kHidden; g.epilogue = EPI_BIAS_GELU;
+        g.lda = kHidden; g.a_rows_alloc = R6; g.C = B("mid"); g.ldc = kFfn; g.M = R6; g.N = kFfn; g.K = kHidden;
+        if (defer) {
+            g.A = B("attn_res"); g.W = w.w1_ln; g.bias = w.ffn_c2; g.c1 = w.ffn_c1; g.stats_in = stats1; g.epilogue = EPI_LN_BIAS_GELU;
+        } else {
+            g.A = B("ln1"); g.W = w.w1; g.bias = w.b1; g.epilogue = EPI_BIAS_GELU;
+        }
         if ((rc = run_gemm(h, g, s))) return rc;
         g = GemmArgs();
         g.A = B("mid"); g.lda = kFfn; g.a_rows_alloc = R6; g.W = w.w2; g.C = B("ffn_res"); g.ldc = kHidden;
-        g.bias = w.b2; g.R = B("ln1"); g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kFfn; g.epilogue = EPI_BIAS_RESIDUAL;
+        g.bias = w.b2; g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kFfn;
+        if (defer) {
+            g.R = B("attn_res"); g.stats_in = stats1; g.ln_gamma = w.ln1_w; g.ln_beta = w.ln1_b; g.stats_out = stats2;
+            g.epilogue = EPI_BIAS_LNRESIDUAL_STATS;
+        } else {
+            g.R = B("ln1"); g.epilogue = EPI_BIAS_RESIDUAL;
+        }
         if ((rc = run_gemm(h, g, s))) return rc;
         const bool last = (l == n_layers - 1) || (l == h->stop_after_layer);
         if (!last) {
-            LAUNCH(CAT_ROWOPS, launch_layernorm(B("ffn_res"), B("x"), w.ln2_w, w.ln2_b, R6, kHidden, s), 1);
+            if (!defer) LAUNCH(CAT_ROWOPS, launch_layernorm(B("ffn_res"), B("x"), w.ln2_w, w.ln2_b, R6, kHidden, s), 1);
         } else {
             // last LayerNorm fused with the masked mean-pool (+ optional compact fp32 last_hidden_state)
             LAUNCH(CAT_ROWOPS, launch_final_ln_pool(B("ffn_res"), w.ln2_w, w.ln2_b, meta, n_utts, pooled_dev, hidden_dev, h->head, s), 1);
@@ -1028,6 +1115,7 @@ int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
     if (!h || !name) return LOCO_ERR_INVALID;
     if (!strcmp(name, "gemm_impl")) h->gemm_impl = (int)value;
     else if (!strcmp(name, "posconv_impl")) h->posconv_impl = (int)value;
+    else if (!strcmp(name, "ln_impl")) h->ln_impl = (int)value;
     else if (!strcmp(name, "attn_impl")) h->attn_impl = (int)value;
     else if (!strcmp(name, "attn_tc_min_frames")) h->attn_tc_min_frames = (int)value;
     else if (!strcmp(name, "attn_tc_lo")) h->attn_tc_lo = (int)value;

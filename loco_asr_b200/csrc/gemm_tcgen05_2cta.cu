@@ -92,11 +92,24 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+struct LnArgs {                       // deferred-LayerNorm operands (GemmArgs of the same names)
+    const float* stats_in;
+    const float* c1;
+    const float* gamma;
+    const float* beta;
+    float* stats_out;
+};
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
-                const float* __restrict__ bias, int M, int N, int K) {
+                const float* __restrict__ bias, const LnArgs ln, int M, int N, int K) {
+    constexpr bool kRes = EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_RESIDUAL_STATS || EPI == EPI_BIAS_LNRESIDUAL_STATS;
+    constexpr bool kGelu = EPI == EPI_BIAS_GELU || EPI == EPI_LN_BIAS_GELU;
+    constexpr bool kLnIn = EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_GELU;          // rows of A are un-normalised: see GemmEpilogue
+    constexpr bool kLnRes = EPI == EPI_BIAS_LNRESIDUAL_STATS;                      // rows of R are un-normalised
+    constexpr bool kStats = EPI == EPI_BIAS_RESIDUAL_STATS || EPI == EPI_BIAS_LNRESIDUAL_STATS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -115,7 +128,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         tma_prefetch_desc(&tma_c);
-        if (EPI == EPI_BIAS_RESIDUAL) tma_prefetch_desc(&tma_r);
+        if (kRes) tma_prefetch_desc(&tma_r);
         for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(smem_u32(&bars->res_full[w]), 1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&bars->full[s]), 1);
@@ -196,7 +209,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         for (int tile = pair; tile < n_tiles; tile += n_pairs) {
             const int m0 = (tile / n_tiles_n) * (2 * BM) + (int)rank * BM + q * 32;
             const int n0 = (tile % n_tiles_n) * BN + half * (BN / 2);
-            if (EPI == EPI_BIAS_RESIDUAL && PANELS == 2) {
+            if (kRes && PANELS == 2) {
                 // both residual panels of this warp's 32 x 128 slice, fetched while the tile's MMAs still run
                 if (lane == 0) {
                     bulk_wait_read<0>();            // the previous tile's stores have finished reading the panels
@@ -206,12 +219,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                 }
                 __syncwarp();
             }
+            // deferred LayerNorm: this thread's row as x * ra + rb = (x - mean) * rstd, from the six (mean, M2) partials
+            float2 ra2 = make_float2(1.f, 1.f), rb2 = make_float2(0.f, 0.f);
+            if (kLnIn || kLnRes) {
+                const int row = min(m0 + lane, M - 1);
+                const float4* sp = reinterpret_cast<const float4*>(ln.stats_in + (int64_t)row * (2 * kStatSlots));
+                const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2);
+                const float mean = (s0.x + s0.z + s1.x + s1.z + s2.x + s2.z) * (1.0f / kStatSlots);
+                float m2 = (s0.y + s0.w) + (s1.y + s1.w) + (s2.y + s2.w);
+                const float d0 = s0.x - mean, d1 = s0.z - mean, d2 = s1.x - mean, d3 = s1.z - mean, d4 = s2.x - mean, d5 = s2.z - mean;
+                m2 = fmaf(128.f, fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, fmaf(d4, d4, d5 * d5))))), m2);
+                const float rstd = rsqrtf(m2 * (1.0f / 768.f) + kLnEps);
+                ra2 = make_float2(rstd, rstd);
+                rb2 = make_float2(-mean * rstd, -mean * rstd);
+            }
+            float2 ssum = make_float2(0.f, 0.f), ssq = make_float2(0.f, 0.f);
             mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
             uint32_t v[2][32];
             tmem_ld_32x32(t_row, v[0]);
-            if (EPI == EPI_BIAS_RESIDUAL && PANELS == 2) {
+            if (kRes && PANELS == 2) {
                 mbar_wait(res_bar, res_phase);
                 res_phase ^= 1u;
             }
@@ -219,14 +247,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             for (int c = 0; c < 4; ++c) {
                 const uint32_t panel = panel0 + (PANELS == 2 ? (c >> 1) * PANEL_BYTES : 0);
                 const uint32_t my_row = panel + lane * 128;
-                if ((c & 1) == 0 && (PANELS == 1 || EPI != EPI_BIAS_RESIDUAL)) {
+                if ((c & 1) == 0 && (PANELS == 1 || !kRes)) {
                     // the TMA store that last read this panel must have finished before it is overwritten
                     if (lane == 0) {
                         if (PANELS == 2) bulk_wait_read<1>();      // only the OTHER panel's store (the most recent group) may be in flight
                         else bulk_wait_read<0>();
                     }
                     __syncwarp();
-                    if (EPI == EPI_BIAS_RESIDUAL && lane == 0) {
+                    if (kRes && lane == 0) {
                         mbar_arrive_expect_tx(res_bar, PANEL_BYTES);
                         tma_load_2d(panel, &tma_r, res_bar, n0 + (c >> 1) * 64, m0);
                     }
@@ -238,7 +266,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                     tc_fence_before();
                     mbar_arrive_cluster(smem_u32(&bars->tmem_empty[acc]) & kPeerMask);      // the leader's barrier
                 }
-                if (EPI == EPI_BIAS_RESIDUAL && PANELS == 1 && (c & 1) == 0) {
+                if (kRes && PANELS == 1 && (c & 1) == 0) {
                     mbar_wait(res_bar, res_phase);
                     res_phase ^= 1u;
                 }
@@ -247,7 +275,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                     float2 f[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) f[e] = make_float2(__uint_as_float(v[c & 1][j + 2 * e]), __uint_as_float(v[c & 1][j + 2 * e + 1]));
-                    if (bias != nullptr) {
+                    if (kLnIn) {
+                        // rstd_r (acc - mean_r c1[n]) + bias[n]
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j + 4));
+                        const float4 k0 = __ldg(reinterpret_cast<const float4*>(ln.c1 + n0 + c * 32 + j));
+                        const float4 k1 = __ldg(reinterpret_cast<const float4*>(ln.c1 + n0 + c * 32 + j + 4));
+                        f[0] = fma_f32x2(f[0], ra2, fma_f32x2(make_float2(k0.x, k0.y), rb2, make_float2(b0.x, b0.y)));
+                        f[1] = fma_f32x2(f[1], ra2, fma_f32x2(make_float2(k0.z, k0.w), rb2, make_float2(b0.z, b0.w)));
+                        f[2] = fma_f32x2(f[2], ra2, fma_f32x2(make_float2(k1.x, k1.y), rb2, make_float2(b1.x, b1.y)));
+                        f[3] = fma_f32x2(f[3], ra2, fma_f32x2(make_float2(k1.z, k1.w), rb2, make_float2(b1.z, b1.w)));
+                    } else if (bias != nullptr) {
                         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j));
                         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + j + 4));
                         f[0] = add_f32x2(f[0], make_float2(b0.x, b0.y));
@@ -255,17 +293,34 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                         f[2] = add_f32x2(f[2], make_float2(b1.x, b1.y));
                         f[3] = add_f32x2(f[3], make_float2(b1.z, b1.w));
                     }
-                    if (EPI == EPI_BIAS_GELU) {
+                    if (kGelu) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) f[e] = gelu_erf2(f[e]);
                     }
                     const uint32_t addr = my_row + ((((c & 1) * 4 + (j >> 3)) ^ (lane & 7)) << 4);
-                    if (EPI == EPI_BIAS_RESIDUAL) {
+                    if (kRes) {
                         const uint4 rr = lds128(addr);
-                        f[0] = add_f32x2(f[0], unpack_bf16(rr.x));
-                        f[1] = add_f32x2(f[1], unpack_bf16(rr.y));
-                        f[2] = add_f32x2(f[2], unpack_bf16(rr.z));
-                        f[3] = add_f32x2(f[3], unpack_bf16(rr.w));
+                        float2 r[4] = {unpack_bf16(rr.x), unpack_bf16(rr.y), unpack_bf16(rr.z), unpack_bf16(rr.w)};
+                        if (kLnRes) {
+                            // the residual is LayerNorm(R): (R - mean_r) rstd_r gamma[n] + beta[n]
+                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(ln.gamma + n0 + c * 32 + j));
+                            const float4 g1 = __ldg(reinterpret_cast<const float4*>(ln.gamma + n0 + c * 32 + j + 4));
+                            const float4 e0 = __ldg(reinterpret_cast<const float4*>(ln.beta + n0 + c * 32 + j));
+                            const float4 e1 = __ldg(reinterpret_cast<const float4*>(ln.beta + n0 + c * 32 + j + 4));
+                            r[0] = fma_f32x2(fma_f32x2(r[0], ra2, rb2), make_float2(g0.x, g0.y), make_float2(e0.x, e0.y));
+                            r[1] = fma_f32x2(fma_f32x2(r[1], ra2, rb2), make_float2(g0.z, g0.w), make_float2(e0.z, e0.w));
+                            r[2] = fma_f32x2(fma_f32x2(r[2], ra2, rb2), make_float2(g1.x, g1.y), make_float2(e1.x, e1.y));
+                            r[3] = fma_f32x2(fma_f32x2(r[3], ra2, rb2), make_float2(g1.z, g1.w), make_float2(e1.z, e1.w));
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) f[e] = add_f32x2(f[e], r[e]);
+                    }
+                    if (kStats) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            ssum = add_f32x2(ssum, f[e]);
+                            ssq = fma_f32x2(f[e], f[e], ssq);
+                        }
                     }
                     uint4 o;
                     o.x = pack_bf16(f[0].x, f[0].y);
@@ -283,6 +338,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                     }
                 }
             }
+            if (kStats) {
+                // (mean, M2) of this row's 128 columns; slot = position of the slice in the 768-wide row
+                const float sum = ssum.x + ssum.y, sq = ssq.x + ssq.y;
+                const float mean_p = sum * (1.0f / 128.f);
+                const int row = m0 + lane;
+                if (row < M)
+                    *reinterpret_cast<float2*>(ln.stats_out + (int64_t)row * (2 * kStatSlots) + 2 * ((tile % n_tiles_n) * 2 + half)) =
+                        make_float2(mean_p, fmaxf(sq - sum * mean_p, 0.f));
+            }
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) bulk_wait<0>();
@@ -299,7 +363,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 template <int EPI>
 int launch2_t(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, int grid,
               cudaStream_t stream) {
-    return launch_pdl(gemm_tc2_kernel<EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, ma, mb, mc, mr, g.bias, g.M, g.N, g.K);
+    const LnArgs ln = {g.stats_in, g.c1, g.ln_gamma, g.ln_beta, g.stats_out};
+    return launch_pdl(gemm_tc2_kernel<EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, ma, mb, mc, mr, g.bias, ln, g.M, g.N, g.K);
 }
 
 }  // namespace
@@ -311,13 +376,27 @@ int gemm_tc2_init() {
     e = cudaFuncSetAttribute(gemm_tc2_kernel<EPI_BIAS_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(gemm_tc2_kernel<EPI_BIAS_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_tc2_kernel<EPI_LN_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_tc2_kernel<EPI_LN_BIAS_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_tc2_kernel<EPI_BIAS_RESIDUAL_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_tc2_kernel<EPI_BIAS_LNRESIDUAL_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     return (int)e;
 }
 
 int gemm_tc2_launch(const GemmArgs& g, int num_sms, cudaStream_t stream) {
     if (g.M <= 0) return 0;
     if (g.N % BN != 0 || g.K % BK != 0 || (g.lda * 2) % 16 != 0 || (g.ldc % 8) != 0) return (int)cudaErrorInvalidValue;
-    if (g.epilogue == EPI_BIAS_RESIDUAL && (g.R == nullptr || (g.ldr % 8) != 0)) return (int)cudaErrorInvalidValue;
+    const bool has_res = g.epilogue == EPI_BIAS_RESIDUAL || g.epilogue == EPI_BIAS_RESIDUAL_STATS || g.epilogue == EPI_BIAS_LNRESIDUAL_STATS;
+    const bool ln_in = g.epilogue == EPI_LN_BIAS || g.epilogue == EPI_LN_BIAS_GELU;
+    const bool stats = g.epilogue == EPI_BIAS_RESIDUAL_STATS || g.epilogue == EPI_BIAS_LNRESIDUAL_STATS;
+    if (has_res && (g.R == nullptr || (g.ldr % 8) != 0)) return (int)cudaErrorInvalidValue;
+    if (ln_in && (!g.stats_in || !g.c1 || !g.bias)) return (int)cudaErrorInvalidValue;
+    if (stats && (!g.stats_out || g.N != kStatSlots * 128)) return (int)cudaErrorInvalidValue;
+    if (g.epilogue == EPI_BIAS_LNRESIDUAL_STATS && (!g.stats_in || !g.ln_gamma || !g.ln_beta)) return (int)cudaErrorInvalidValue;
     alignas(64) CUtensorMap ma, mb, mc, mr;
     int rc = make_tensor_map_bf16_sw128(&ma, g.A, (uint64_t)g.K, (uint64_t)g.a_rows_alloc, (uint64_t)g.lda, BM);
     if (rc) return rc;
@@ -326,7 +405,7 @@ int gemm_tc2_launch(const GemmArgs& g, int num_sms, cudaStream_t stream) {
     rc = make_tensor_map_bf16_sw128(&mc, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc, 32);
     if (rc) return rc;
     mr = mc;
-    if (g.epilogue == EPI_BIAS_RESIDUAL) {
+    if (has_res) {
         rc = make_tensor_map_bf16_sw128(&mr, g.R, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldr, 32);
         if (rc) return rc;
     }
@@ -336,6 +415,10 @@ int gemm_tc2_launch(const GemmArgs& g, int num_sms, cudaStream_t stream) {
         case EPI_BIAS: return launch2_t<EPI_BIAS>(g, ma, mb, mc, mr, grid, stream);
         case EPI_BIAS_GELU: return launch2_t<EPI_BIAS_GELU>(g, ma, mb, mc, mr, grid, stream);
         case EPI_BIAS_RESIDUAL: return launch2_t<EPI_BIAS_RESIDUAL>(g, ma, mb, mc, mr, grid, stream);
+        case EPI_LN_BIAS: return launch2_t<EPI_LN_BIAS>(g, ma, mb, mc, mr, grid, stream);
+        case EPI_LN_BIAS_GELU: return launch2_t<EPI_LN_BIAS_GELU>(g, ma, mb, mc, mr, grid, stream);
+        case EPI_BIAS_RESIDUAL_STATS: return launch2_t<EPI_BIAS_RESIDUAL_STATS>(g, ma, mb, mc, mr, grid, stream);
+        case EPI_BIAS_LNRESIDUAL_STATS: return launch2_t<EPI_BIAS_LNRESIDUAL_STATS>(g, ma, mb, mc, mr, grid, stream);
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -14,7 +14,14 @@ enum GemmEpilogue : int {
     EPI_BIAS = 0,           // C = A W^T (+ bias)
     EPI_BIAS_GELU = 1,      // C = gelu(A W^T (+ bias))
     EPI_BIAS_RESIDUAL = 2,  // C = A W^T + bias + R
+    // Deferred LayerNorm (CTA-pair kernel only; N = 768 producers, any N consumers).  A post-LN block x' = LN(u), u = x + f(x),
+    // never materialises x': the producer writes u and per-row partial statistics, the consumers normalise on the fly.
+    EPI_LN_BIAS = 3,                 // C = rstd_r (A W'^T - mean_r c1[n]) + bias[n]        A = u (un-normalised), W' = gamma (.) W,
+    EPI_LN_BIAS_GELU = 4,            // C = gelu(same)                                      c1[n] = sum_k W'[n,k], bias = beta W^T + b
+    EPI_BIAS_RESIDUAL_STATS = 5,     // C = A W^T + bias + R, and the row statistics of C
+    EPI_BIAS_LNRESIDUAL_STATS = 6,   // C = A W^T + bias + ((R - mean_r) rstd_r gamma[n] + beta[n]), and the row statistics of C
 };
+constexpr int kStatSlots = 6;        // row statistics of an [M, 768] tensor: (mean, M2) of each 128-column slice, kStatSlots * 2 floats per row
 
 // One GEMM problem: C[M, N] (bf16, row stride ldc) = epi(A[M, K] * W[N, K]^T).
 // A rows may overlap in memory (lda < K) -- that is how the strided convolutions are expressed
@@ -31,6 +38,12 @@ struct GemmArgs {
     int64_t ldr;
     int M, N, K;
     int epilogue;
+    // deferred-LayerNorm epilogues
+    const float* stats_in = nullptr;   // [M, kStatSlots, 2] statistics of the rows of A (EPI_LN_*) or of R (EPI_BIAS_LNRESIDUAL_STATS)
+    const float* c1 = nullptr;         // [N] column sums of W' (EPI_LN_*)
+    const float* ln_gamma = nullptr;   // [N] affine of the LayerNorm applied to R (EPI_BIAS_LNRESIDUAL_STATS)
+    const float* ln_beta = nullptr;
+    float* stats_out = nullptr;        // [M, kStatSlots, 2] statistics of the rows of C (EPI_*_STATS; N must be 768)
 };
 
 // Launch helper.  With LOCO_PDL=1 kernels are launched with programmatic stream serialization (PDL): a kernel may be
