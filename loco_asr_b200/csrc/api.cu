@@ -33,6 +33,7 @@ struct LayerW {
     // c1[n] = sum_k W'[n, k] (of the bf16-rounded W', so the mean term cancels exactly) and c2[n] = sum_k beta[k] W[n, k] + b[n]
     bf16 *wqkv_ln = nullptr, *w1_ln = nullptr;       // wqkv_ln: layers >= 1 (final_layer_norm of the layer before)
     float *qkv_c1 = nullptr, *qkv_c2 = nullptr, *ffn_c1 = nullptr, *ffn_c2 = nullptr;
+    float *bo_ln = nullptr, *b2_ln = nullptr;        // out_proj / FFN2 bias plus the beta of the LayerNorm their residual goes through
 };
 
 struct Buf {
@@ -728,6 +729,11 @@ int loco_finalize_weights(loco_handle* h) {
             if ((rc = get(h, p + "layer_norm.bias", {768}, &be1))) return rc;
             if ((rc = fold(w1t->data.data(), b1t->data.data(), g1->data.data(), be1->data.data(), 3072, 1.0f, 0, &w.w1_ln, &w.ffn_c1, &w.ffn_c2)))
                 return rc;
+            const HostTensor* b2t;
+            if ((rc = get(h, p + "feed_forward.output_dense.bias", {768}, &b2t))) return rc;
+            std::vector<float> bb(768);
+            for (int i = 0; i < 768; ++i) bb[i] = b2t->data[i] + be1->data[i];
+            if ((rc = upload(h, bb, &w.b2_ln))) return rc;
         }
         if (l > 0) {
             const std::string pp = "wrapped_encoder.layers." + std::to_string(l - 1) + ".";
@@ -743,6 +749,11 @@ int loco_finalize_weights(loco_handle* h) {
             memcpy(bcat.data() + 1536, bv->data.data(), 768 * sizeof(float));
             if ((rc = fold(wcat.data(), bcat.data(), g2->data.data(), be2->data.data(), 2304, kQScale, 768, &w.wqkv_ln, &w.qkv_c1, &w.qkv_c2)))
                 return rc;
+            const HostTensor* bot;
+            if ((rc = get(h, p + "attention.out_proj.bias", {768}, &bot))) return rc;
+            std::vector<float> bb(768);
+            for (int i = 0; i < 768; ++i) bb[i] = bot->data[i] + be2->data[i];
+            if ((rc = upload(h, bb, &w.bo_ln))) return rc;
         }
     }
     if (h->has_speech && (rc = build_sin_table(h, h->cfg.max_speech_positions + h->cfg.pad_token_id + 3))) return rc;
@@ -821,7 +832,7 @@ static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, f
         g.A = B("ctx"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wo; g.C = B("attn_res"); g.ldc = kHidden;
         g.bias = w.bo; g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kHidden;
         if (ln_in) {
-            g.R = B("ffn_res"); g.stats_in = stats2; g.ln_gamma = wp.ln2_w; g.ln_beta = wp.ln2_b; g.stats_out = stats1;
+            g.R = B("ffn_res"); g.stats_in = stats2; g.ln_gamma = wp.ln2_w; g.bias = w.bo_ln; g.stats_out = stats1;
             g.epilogue = EPI_BIAS_LNRESIDUAL_STATS;
         } else {
             g.R = B("x"); g.stats_out = stats1; g.epilogue = defer ? EPI_BIAS_RESIDUAL_STATS : EPI_BIAS_RESIDUAL;
@@ -840,7 +851,7 @@ static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, f
         g.A = B("mid"); g.lda = kFfn; g.a_rows_alloc = R6; g.W = w.w2; g.C = B("ffn_res"); g.ldc = kHidden;
         g.bias = w.b2; g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kFfn;
         if (defer) {
-            g.R = B("attn_res"); g.stats_in = stats1; g.ln_gamma = w.ln1_w; g.ln_beta = w.ln1_b; g.stats_out = stats2;
+            g.R = B("attn_res"); g.stats_in = stats1; g.ln_gamma = w.ln1_w; g.bias = w.b2_ln; g.stats_out = stats2;
             g.epilogue = EPI_BIAS_LNRESIDUAL_STATS;
         } else {
             g.R = B("ln1"); g.epilogue = EPI_BIAS_RESIDUAL;

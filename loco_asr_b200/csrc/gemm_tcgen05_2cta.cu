@@ -96,7 +96,6 @@ struct LnArgs {                       // deferred-LayerNorm operands (GemmArgs o
     const float* stats_in;
     const float* c1;
     const float* gamma;
-    const float* beta;
     float* stats_out;
 };
 
@@ -302,18 +301,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                         const uint4 rr = lds128(addr);
                         float2 r[4] = {unpack_bf16(rr.x), unpack_bf16(rr.y), unpack_bf16(rr.z), unpack_bf16(rr.w)};
                         if (kLnRes) {
-                            // the residual is LayerNorm(R): (R - mean_r) rstd_r gamma[n] + beta[n]
+                            // the residual is LayerNorm(R) = ((R - mean_r) rstd_r) gamma[n] + beta[n]; beta travels inside `bias`
                             const float4 g0 = __ldg(reinterpret_cast<const float4*>(ln.gamma + n0 + c * 32 + j));
                             const float4 g1 = __ldg(reinterpret_cast<const float4*>(ln.gamma + n0 + c * 32 + j + 4));
-                            const float4 e0 = __ldg(reinterpret_cast<const float4*>(ln.beta + n0 + c * 32 + j));
-                            const float4 e1 = __ldg(reinterpret_cast<const float4*>(ln.beta + n0 + c * 32 + j + 4));
-                            r[0] = fma_f32x2(fma_f32x2(r[0], ra2, rb2), make_float2(g0.x, g0.y), make_float2(e0.x, e0.y));
-                            r[1] = fma_f32x2(fma_f32x2(r[1], ra2, rb2), make_float2(g0.z, g0.w), make_float2(e0.z, e0.w));
-                            r[2] = fma_f32x2(fma_f32x2(r[2], ra2, rb2), make_float2(g1.x, g1.y), make_float2(e1.x, e1.y));
-                            r[3] = fma_f32x2(fma_f32x2(r[3], ra2, rb2), make_float2(g1.z, g1.w), make_float2(e1.z, e1.w));
-                        }
+                            f[0] = fma_f32x2(fma_f32x2(r[0], ra2, rb2), make_float2(g0.x, g0.y), f[0]);
+                            f[1] = fma_f32x2(fma_f32x2(r[1], ra2, rb2), make_float2(g0.z, g0.w), f[1]);
+                            f[2] = fma_f32x2(fma_f32x2(r[2], ra2, rb2), make_float2(g1.x, g1.y), f[2]);
+                            f[3] = fma_f32x2(fma_f32x2(r[3], ra2, rb2), make_float2(g1.z, g1.w), f[3]);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) f[e] = add_f32x2(f[e], r[e]);
+                            for (int e = 0; e < 4; ++e) f[e] = add_f32x2(f[e], r[e]);
+                        }
                     }
                     if (kStats) {
 #pragma unroll
@@ -363,7 +361,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 template <int EPI>
 int launch2_t(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr, int grid,
               cudaStream_t stream) {
-    const LnArgs ln = {g.stats_in, g.c1, g.ln_gamma, g.ln_beta, g.stats_out};
+    const LnArgs ln = {g.stats_in, g.c1, g.ln_gamma, g.stats_out};
     return launch_pdl(gemm_tc2_kernel<EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, ma, mb, mc, mr, g.bias, ln, g.M, g.N, g.K);
 }
 
@@ -396,7 +394,7 @@ int gemm_tc2_launch(const GemmArgs& g, int num_sms, cudaStream_t stream) {
     if (has_res && (g.R == nullptr || (g.ldr % 8) != 0)) return (int)cudaErrorInvalidValue;
     if (ln_in && (!g.stats_in || !g.c1 || !g.bias)) return (int)cudaErrorInvalidValue;
     if (stats && (!g.stats_out || g.N != kStatSlots * 128)) return (int)cudaErrorInvalidValue;
-    if (g.epilogue == EPI_BIAS_LNRESIDUAL_STATS && (!g.stats_in || !g.ln_gamma || !g.ln_beta)) return (int)cudaErrorInvalidValue;
+    if (g.epilogue == EPI_BIAS_LNRESIDUAL_STATS && (!g.stats_in || !g.ln_gamma || !g.bias)) return (int)cudaErrorInvalidValue;
     alignas(64) CUtensorMap ma, mb, mc, mr;
     int rc = make_tensor_map_bf16_sw128(&ma, g.A, (uint64_t)g.K, (uint64_t)g.a_rows_alloc, (uint64_t)g.lda, BM);
     if (rc) return rc;

@@ -19,7 +19,7 @@ enum GemmEpilogue : int {
     EPI_LN_BIAS = 3,                 // C = rstd_r (A W'^T - mean_r c1[n]) + bias[n]        A = u (un-normalised), W' = gamma (.) W,
     EPI_LN_BIAS_GELU = 4,            // C = gelu(same)                                      c1[n] = sum_k W'[n,k], bias = beta W^T + b
     EPI_BIAS_RESIDUAL_STATS = 5,     // C = A W^T + bias + R, and the row statistics of C
-    EPI_BIAS_LNRESIDUAL_STATS = 6,   // C = A W^T + bias + ((R - mean_r) rstd_r gamma[n] + beta[n]), and the row statistics of C
+    EPI_BIAS_LNRESIDUAL_STATS = 6,   // C = A W^T + bias' + (R - mean_r) rstd_r gamma[n], bias' = bias + beta, and the row statistics of C
 };
 constexpr int kStatSlots = 6;        // row statistics of an [M, 768] tensor: (mean, M2) of each 128-column slice, kStatSlots * 2 floats per row
 
@@ -41,8 +41,7 @@ struct GemmArgs {
     // deferred-LayerNorm epilogues
     const float* stats_in = nullptr;   // [M, kStatSlots, 2] statistics of the rows of A (EPI_LN_*) or of R (EPI_BIAS_LNRESIDUAL_STATS)
     const float* c1 = nullptr;         // [N] column sums of W' (EPI_LN_*)
-    const float* ln_gamma = nullptr;   // [N] affine of the LayerNorm applied to R (EPI_BIAS_LNRESIDUAL_STATS)
-    const float* ln_beta = nullptr;
+    const float* ln_gamma = nullptr;   // [N] scale of the LayerNorm applied to R (EPI_BIAS_LNRESIDUAL_STATS; its shift is folded into bias)
     float* stats_out = nullptr;        // [M, kStatSlots, 2] statistics of the rows of C (EPI_*_STATS; N must be 768)
 };
 
