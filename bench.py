@@ -263,7 +263,7 @@ def main():
     # DRAM bytes per GEMM launch come from the committed ncu capture of the same command (profiles/), never from this run
     gemm_traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01f_gemm_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r01g_gemm_traffic.json")) as fh:
             tj = json.load(fh)
         gemm_traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"]
     except (OSError, KeyError, ValueError):
