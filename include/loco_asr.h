@@ -184,6 +184,13 @@ LOCO_API int loco_debug_buffer(loco_handle* h, const char* name, void** dev_ptr,
 LOCO_API int loco_debug_gemm(loco_handle* h, int impl, const void* a_bf16, int64_t lda, int64_t a_rows_alloc, const void* w_bf16,
                     void* c_bf16, const float* bias, const void* r_bf16, int m, int n, int k, int epilogue, void* stream);
 
+/* The deferred-LayerNorm epilogues of the CTA-pair GEMM (epilogue 3..6, see csrc/internal.h GemmEpilogue), N = 768 where
+ * statistics are produced.  stats_in / stats_out: f32[M, 6, 2] = (mean, M2) of each 128-column slice of a 768-wide row;
+ * c1: f32[N] column sums of W; gamma: f32[N].  Unused operands may be NULL. */
+LOCO_API int loco_debug_gemm_ln(loco_handle* h, const void* a_bf16, const void* w_bf16, void* c_bf16, const float* bias,
+                                const void* r_bf16, int m, int n, int k, int epilogue, const float* stats_in, const float* c1,
+                                const float* gamma, float* stats_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

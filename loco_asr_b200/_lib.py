@@ -15,6 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 LOCO_F32, LOCO_F16, LOCO_BF16, LOCO_F64 = 0, 1, 2, 3
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
+EPI_LN_BIAS, EPI_LN_BIAS_GELU, EPI_BIAS_RESIDUAL_STATS, EPI_BIAS_LNRESIDUAL_STATS = 3, 4, 5, 6
 
 
 class LocoError(RuntimeError):
@@ -58,6 +59,8 @@ SIGNATURES = {
     "loco_debug_buffer": (C.c_int, [_H, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "loco_debug_gemm": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "loco_debug_gemm_ln": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

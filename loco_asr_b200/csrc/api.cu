@@ -1163,4 +1163,20 @@ int loco_debug_gemm(loco_handle* h, int impl, const void* a, int64_t lda, int64_
     return rc;
 }
 
+int loco_debug_gemm_ln(loco_handle* h, const void* a, const void* w, void* c, const float* bias, const void* r, int m, int n, int k,
+                       int epilogue, const float* stats_in, const float* c1, const float* gamma, float* stats_out, void* stream) {
+    if (!h) return LOCO_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    GemmArgs g = {};
+    g.A = reinterpret_cast<const bf16*>(a); g.lda = k; g.a_rows_alloc = m;
+    g.W = reinterpret_cast<const bf16*>(w); g.C = reinterpret_cast<bf16*>(c); g.ldc = n; g.bias = bias;
+    g.R = reinterpret_cast<const bf16*>(r); g.ldr = n; g.M = m; g.N = n; g.K = k; g.epilogue = epilogue;
+    g.stats_in = stats_in; g.c1 = c1; g.ln_gamma = gamma; g.stats_out = stats_out;
+    const int saved = h->gemm_impl;
+    h->gemm_impl = 2;
+    int rc = run_gemm(h, g, reinterpret_cast<cudaStream_t>(stream));
+    h->gemm_impl = saved;
+    return rc;
+}
+
 }  // extern "C"

@@ -453,6 +453,21 @@ class LocoSpeechT5Encoder:
         _lib.check(self._lib, self._h, rc, "loco_debug_gemm")
         return c
 
+    def debug_gemm_ln(self, a, w, epilogue, bias=None, residual=None, stats_in=None, c1=None, gamma=None, want_stats=False):
+        """Unit-test entry for the deferred-LayerNorm epilogues of the CTA-pair GEMM (csrc/internal.h GemmEpilogue 3..6).
+        Returns C bf16 [M, N] (and the row statistics f32 [M, 6, 2] when asked)."""
+        m, k = a.shape
+        n = w.shape[0]
+        c = torch.empty(m, n, dtype=torch.bfloat16, device=self.device)
+        stats = torch.zeros(m, 6, 2, dtype=torch.float32, device=self.device) if want_stats else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = self._lib.loco_debug_gemm_ln(self._h, a.data_ptr(), w.data_ptr(), c.data_ptr(), ptr(bias), ptr(residual), m, n, k,
+                                              epilogue, ptr(stats_in), ptr(c1), ptr(gamma), ptr(stats), C.c_void_p(stream))
+        _lib.check(self._lib, self._h, rc, "loco_debug_gemm_ln")
+        return (c, stats) if want_stats else c
+
     PROFILE_CATEGORIES = ("gemm", "attention", "pos_conv", "frontend", "rowops")
 
     def profile_enable(self, on: bool = True):

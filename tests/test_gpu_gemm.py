@@ -60,3 +60,59 @@ def test_gemm_without_bias(encoder):
     c = encoder.debug_gemm(a, w, bias=None, epilogue=_lib.EPI_BIAS_GELU, impl=2)
     ref = torch.nn.functional.gelu(a.float() @ w.float().t())
     assert float((c.float() - ref).abs().max()) < 0.03
+
+
+def _row_stats(x):
+    """(mean, M2) of each 128-column slice of the 768-wide rows of x: the layout the GEMM epilogues exchange."""
+    xs = x.double().reshape(x.shape[0], 6, 128)
+    mean = xs.mean(dim=2)
+    return torch.stack([mean, ((xs - mean[:, :, None]) ** 2).sum(dim=2)], dim=2).float()
+
+
+@pytest.mark.parametrize("M", [1, 300, 40000])
+def test_deferred_layernorm_epilogues(encoder, M):
+    """The four epilogues that replace the LayerNorm kernels of the transformer layers, each against torch:
+    producer (C = A W^T + b + R and its row statistics), consumer (rstd (A W'^T - mean c1) + c2, optionally GELU), and the
+    producer whose residual is itself un-normalised ((R - mean) rstd gamma, beta inside the bias).  Rows carry a mean of
+    up to +-3 sigma-units so the mean terms matter."""
+    g = torch.Generator(device="cuda").manual_seed(1000 + M)
+    rnd = lambda *shape: torch.randn(*shape, device="cuda", generator=g)
+    K = 768
+    # ---- producer: out_proj-like, plain residual, statistics out
+    a = rnd(M, K).bfloat16()
+    w = (rnd(768, K) * 0.05).bfloat16()
+    bias = rnd(768) * 0.1
+    res = (rnd(M, 768) + 3.0 * rnd(M, 1)).bfloat16()
+    u_ref = a.float() @ w.float().t() + bias + res.float()
+    u, stats = encoder.debug_gemm_ln(a, w, _lib.EPI_BIAS_RESIDUAL_STATS, bias=bias, residual=res, want_stats=True)
+    tol = lambda ref: ref.abs() * 2 ** -8 + 4e-3
+    assert bool(((u.float() - u_ref).abs() <= tol(u_ref)).all())
+    want = _row_stats(u_ref)
+    assert torch.allclose(stats[:, :, 0], want[:, :, 0], rtol=0, atol=2e-4)
+    assert torch.allclose(stats[:, :, 1], want[:, :, 1], rtol=2e-3, atol=2e-2)
+    # ---- consumers: FFN1-like, A = the un-normalised u with its statistics
+    gamma, beta = 1.0 + 0.2 * rnd(768), 0.2 * rnd(768)
+    w1 = rnd(3072, 768) * 0.05
+    b1 = rnd(3072) * 0.1
+    w1f = (w1 * gamma).bfloat16()
+    c1 = w1f.float().sum(dim=1)
+    c2 = w1 @ beta + b1
+    x_ln = torch.nn.functional.layer_norm(u.float(), (768,), gamma, beta, 1e-5)
+    ref = x_ln @ w1.t() + b1
+    for epi, fn in ((_lib.EPI_LN_BIAS, lambda t: t), (_lib.EPI_LN_BIAS_GELU, torch.nn.functional.gelu)):
+        got = encoder.debug_gemm_ln(u, w1f, epi, bias=c2, stats_in=stats, c1=c1)
+        r = fn(ref)
+        # bf16 rounding of gamma (.) W against fp32 W of the reference, K = 768 terms, plus the output rounding
+        assert float((got.float() - r).abs().max()) < 0.06 and float((got.float() - r).abs().mean()) < 4e-3
+    # ---- producer with an un-normalised residual: FFN2-like
+    a2 = rnd(M, 256).bfloat16()
+    w2 = (rnd(768, 256) * 0.05).bfloat16()
+    b2 = rnd(768) * 0.1
+    v_ref = a2.float() @ w2.float().t() + b2 + x_ln
+    v, stats2 = encoder.debug_gemm_ln(a2, w2, _lib.EPI_BIAS_LNRESIDUAL_STATS, bias=b2 + beta, residual=u, stats_in=stats, gamma=gamma,
+                                      want_stats=True)
+    assert bool(((v.float() - v_ref).abs() <= tol(v_ref) + 4e-3).all())
+    want2 = _row_stats(v_ref)
+    # (the kernel normalises R with the statistics of the producer's fp32 values, torch with those of the bf16-rounded u)
+    assert torch.allclose(stats2[:, :, 0], want2[:, :, 0], rtol=0, atol=4e-3)
+    assert torch.allclose(stats2[:, :, 1], want2[:, :, 1], rtol=1e-2, atol=0.2)
