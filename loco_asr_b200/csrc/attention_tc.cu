@@ -39,8 +39,8 @@
 // pv_done.  Every softmax thread runs the same barrier skeleton whether or not its rows exist, and no waiter can be lapped
 // by two phases of its barrier (see ga_empty / o_full).  Set LOCO_ATTN_DEBUG=1 to have a stuck wait reported per role.
 //
-// Measured (tools/attn_sweep.py, 64k frames per batch, per layer): 0.36 ms at T = 256, 0.51 ms at 499, 0.95 ms at 1499,
-// 1.59 ms at 2999 (384 TFLOP/s of Q K^T + P V + table FLOPs) -- 1.5-1.95x the mma.sync kernel; where a 128-query tile is mostly
+// Measured (tools/attn_sweep.py, 64k frames per batch, per layer): 0.24 ms at T = 128, 0.31 ms at 256, 0.47 ms at 499, 0.94 ms
+// at 1499, 1.60 ms at 2999 (380 TFLOP/s of Q K^T + P V + table FLOPs) -- 1.3-2x the mma.sync kernel; where a 128-query tile is mostly
 // empty (< 84 or 129..192 frames) the per-item fixed costs (drain, epilogue, ~10 barrier hand-offs) dominate and the
 // mma.sync kernel (attention.cu) takes the utterance (chosen per utterance in loco_encode).
 #include <cuda_fp16.h>
