@@ -97,7 +97,7 @@ struct loco_handle {
     int ln_impl = 0;            // 0 = LayerNorms of the transformer layers deferred into the GEMM epilogues [default], 1 = LayerNorm kernels
     int attn_impl = -1;         // -1 = by length (tcgen05 from attn_tc_min_frames), 0 = tcgen05, 1 = mma.sync
     int attn_tc_min_frames = 193;   // utterances with at least this many frames use the tcgen05 attention kernel,
-    int attn_tc_lo = 84, attn_tc_hi = 128;   // ... and so do utterances that fill most of one 128-query tile (see loco_encode)
+    int attn_tc_lo = 76, attn_tc_hi = 128;   // ... and so do utterances that fill most of one 128-query tile (see loco_encode)
     alignas(64) CUtensorMap pe_map;   // pe_k [320, 64] for the tcgen05 attention kernel
     int stop_after_layer = -1;
     Layout last;
@@ -772,8 +772,8 @@ static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, f
     const int R6 = (int)L.R6;
     // ---- attention work lists.  The kernel is chosen PER UTTERANCE by its own frame count, never by its batch-mates, so
     // an utterance's result does not depend on the batch it travels in.  Measured with tools/attn_sweep.py (ms per layer
-    // at 64k frames, tcgen05 / mma.sync): 64 frames 0.33 / 0.20, 96: 0.26 / 0.28, 128: 0.25 / 0.31, 136: 0.50 / 0.41,
-    // 192: 0.44 / 0.38, 224: 0.40 / 0.54, 499: 0.51 / 0.85, 2999: 1.56 / 3.10.  The persistent tcgen05 kernel pays a fixed
+    // at 64k frames, tcgen05 / mma.sync): 64 frames 0.36 / 0.22, 72: 0.34 / 0.34, 80: 0.31 / 0.32, 96: 0.28 / 0.31, 128: 0.24 / 0.31,
+    // 132: 0.58 / 0.44, 160: 0.50 / 0.40, 192: 0.45 / 0.40, 208: 0.42 / 0.51, 499: 0.47 / 0.87, 2999: 1.60 / 3.3.  The persistent tcgen05 kernel pays a fixed
     // cost per 128-query tile, so it loses where the second tile is mostly empty (129..192 frames) and on very short
     // utterances; the mma.sync kernel works in 64-query tiles, 3-4 CTAs/SM.
     std::vector<PcTile> at_tiles;

@@ -41,7 +41,7 @@
 //
 // Measured (tools/attn_sweep.py, 64k frames per batch, per layer): 0.24 ms at T = 128, 0.31 ms at 256, 0.47 ms at 499, 0.94 ms
 // at 1499, 1.60 ms at 2999 (380 TFLOP/s of Q K^T + P V + table FLOPs) -- 1.3-2x the mma.sync kernel; where a 128-query tile is mostly
-// empty (< 84 or 129..192 frames) the per-item fixed costs (drain, epilogue, ~10 barrier hand-offs) dominate and the
+// empty (< 76 or 129..192 frames) the per-item fixed costs (drain, epilogue, ~10 barrier hand-offs) dominate and the
 // mma.sync kernel (attention.cu) takes the utterance (chosen per utterance in loco_encode).
 #include <cuda_fp16.h>
 #include <stdlib.h>
