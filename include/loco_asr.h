@@ -172,7 +172,7 @@ LOCO_API int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_
 /* ---- debug / test hooks (not part of the product surface) ------------------------------------------- */
 /* name: "gemm_impl" (2 = tcgen05 CTA pair, cta_group::2 [default], 0 = tcgen05 single CTA, 1 = SIMT reference), "posconv_impl" (0 = tcgen05 [default],
  * 1 = mma.sync cross-check), "ln_impl" (0 = the transformer layers' LayerNorms deferred into the GEMM epilogues [default, needs gemm_impl 2],
- * 1 = LayerNorm kernels), "attn_impl" (-1 = by the batch's longest utterance [default], 0 = tcgen05, 1 = mma.sync), "attn_tc_min_frames" / "attn_tc_lo" / "attn_tc_hi" (the frame ranges that select the tcgen05 kernel), "stop_after_layer"
+ * 1 = LayerNorm kernels), "attn_impl" (-1 = per utterance by its own frame count [default], 0 = tcgen05, 1 = mma.sync), "attn_tc_min_frames" / "attn_tc_lo" / "attn_tc_hi" (the frame ranges that select the tcgen05 kernel), "stop_after_layer"
  * (-1 = run all).  */
 LOCO_API int loco_debug_set(loco_handle* h, const char* name, int64_t value);
 /* After an encode: device pointer / geometry of a named stage buffer inside the caller's workspace
