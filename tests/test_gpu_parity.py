@@ -346,3 +346,34 @@ def test_full_size_batch_is_bit_identical_to_single_utterance_encodes(encoder, m
     for u in sorted(set(np.linspace(0, len(lengths) - 1, 12).astype(int).tolist()) | {1, len(lengths) - 2}):
         alone = encoder.encode_packed(wave[int(offs[u]):int(offs[u + 1])].contiguous(), [lengths[u]])
         assert torch.equal(alone[0], pooled[u]), u
+
+
+def test_parity_with_large_layernorm_affines_and_biases(weights):
+    """Random init leaves every LayerNorm at gamma = 1, beta = 0 and every bias near 0, which would hide mistakes in the
+    deferred-LayerNorm algebra (gamma folded into the consumer's weights, beta into biases, the mean term through c1).  Here
+    the affines and biases are drawn wide (gamma 1 +- 0.4, beta +- 0.5, dense biases +- 0.3, so rows carry real means) and the
+    result is held to the same bars against the oracle."""
+    from loco_asr_b200.encoder import LocoSpeechT5Encoder
+    g = torch.Generator().manual_seed(99)
+    sd = {k: v.clone() for k, v in weights.items()}
+    for k in sd:
+        if "layer_norm.weight" in k and "feature_encoder" not in k:
+            sd[k] = 1.0 + 0.4 * (torch.rand(sd[k].shape, generator=g) * 2 - 1)
+        elif "layer_norm.bias" in k and "feature_encoder" not in k:
+            sd[k] = 0.5 * (torch.rand(sd[k].shape, generator=g) * 2 - 1)
+        elif k.startswith("wrapped_encoder.layers.") and k.endswith(".bias"):
+            sd[k] = 0.3 * (torch.rand(sd[k].shape, generator=g) * 2 - 1)
+    enc = LocoSpeechT5Encoder.from_state_dict(sd, device="cuda:0")
+    waves = H.make_waves([9000, 33000, 70000], seed=53)
+    pooled, hidden, info = H.run_encoder(enc, waves)
+    off = 0
+    for u, w in enumerate(waves):
+        ref = O.encode_utterance(sd, torch.from_numpy(w))
+        T = ref.shape[0]
+        assert H.cosine(pooled[u], ref.mean(0)) >= COS_MIN, u
+        assert H.rel_err(pooled[u], ref.mean(0)) < POOLED_REL_MAX, u
+        assert H.rel_err(hidden[off:off + T], ref) < 5e-2, u
+        off += T
+    enc.debug_set("ln_impl", 1)
+    p1, h1, _ = H.run_encoder(enc, waves)
+    assert H.rel_err(hidden, h1) < 3e-2
