@@ -377,3 +377,35 @@ def test_parity_with_large_layernorm_affines_and_biases(weights):
     enc.debug_set("ln_impl", 1)
     p1, h1, _ = H.run_encoder(enc, waves)
     assert H.rel_err(hidden, h1) < 3e-2
+
+
+def test_no_write_outside_the_callers_buffers(encoder):
+    """The caller owns workspace and outputs (include/loco_asr.h): with exactly-sized buffers embedded between guard
+    pages, a ragged batch (1-frame utterance, tile-boundary lengths, a 10 s one) leaves every guard byte untouched --
+    the TMA stores, the padded conv rows and the packed outputs all stay inside what loco_plan announced."""
+    import ctypes as C
+    lengths = [400, 41200, 41520, 64000, 160000, 7777]
+    ns = np.ascontiguousarray(np.asarray(lengths, dtype=np.int32))
+    n = len(lengths)
+    info = encoder.plan(ns)
+    G = 1 << 16
+    ws = torch.full((info["workspace_bytes"] + 2 * G,), 0xAB, dtype=torch.uint8, device="cuda")
+    assert ws.data_ptr() % 1024 == 0
+    pooled = torch.full((n * 768 + 2 * 1024,), 7.25, dtype=torch.float32, device="cuda")
+    hidden = torch.full((info["total_frames"] * 768 + 2 * 1024,), 7.25, dtype=torch.float32, device="cuda")
+    wave = torch.cat([torch.full((1024,), 3.0, device="cuda"), torch.randn(int(ns.sum()), device="cuda") * 0.1,
+                      torch.full((1024,), 3.0, device="cuda")])
+    with torch.cuda.device(encoder.device):
+        rc = encoder._lib.loco_encode(encoder._h, wave.data_ptr() + 4096, ns.ctypes.data, n, pooled.data_ptr() + 4096,
+                                      hidden.data_ptr() + 4096, ws.data_ptr() + G, info["workspace_bytes"],
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert bool((ws[:G] == 0xAB).all()) and bool((ws[-G:] == 0xAB).all())
+    assert bool((pooled[:1024] == 7.25).all()) and bool((pooled[-1024:] == 7.25).all())
+    assert bool((hidden[:1024] == 7.25).all()) and bool((hidden[-1024:] == 7.25).all())
+    assert bool((wave[:1024] == 3.0).all()) and bool((wave[-1024:] == 3.0).all())
+    got = pooled[1024:-1024].reshape(n, 768)
+    assert bool(torch.isfinite(got).all())
+    ref = encoder.encode_packed(wave[1024:-1024].contiguous(), lengths)
+    assert torch.equal(got, ref)          # and the guard pages' contents (a neighbour's 3.0 samples) never leaked in
