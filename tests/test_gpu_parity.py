@@ -409,3 +409,26 @@ def test_no_write_outside_the_callers_buffers(encoder):
     assert bool(torch.isfinite(got).all())
     ref = encoder.encode_packed(wave[1024:-1024].contiguous(), lengths)
     assert torch.equal(got, ref)          # and the guard pages' contents (a neighbour's 3.0 samples) never leaked in
+
+
+@pytest.mark.parametrize("fill", [0x00, 0xFF, 0x7F])
+def test_result_does_not_depend_on_workspace_contents(encoder, fill):
+    """Nothing reads workspace bytes it has not written: the same ragged batch over a workspace pre-filled with zeros,
+    with 0xFF (bf16 / fp32 NaN patterns) or with 0x7F7F (huge finite bf16) gives bit-identical results -- slot padding
+    rows, TMA boxes that reach past an utterance and masked keys included."""
+    import ctypes as C
+    lengths = [400, 12000, 41200, 41520, 64000, 100000, 7777, 30000]
+    ns = np.ascontiguousarray(np.asarray(lengths, dtype=np.int32))
+    n = len(lengths)
+    info = encoder.plan(ns)
+    wave = torch.randn(int(ns.sum()), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) * 0.1
+    want_p, want_h, _ = encoder.encode_packed(wave, lengths, return_hidden=True)
+    ws = torch.full((info["workspace_bytes"],), fill, dtype=torch.uint8, device="cuda")
+    pooled = torch.empty(n, 768, device="cuda")
+    hidden = torch.empty(info["total_frames"], 768, device="cuda")
+    with torch.cuda.device(encoder.device):
+        rc = encoder._lib.loco_encode(encoder._h, wave.data_ptr(), ns.ctypes.data, n, pooled.data_ptr(), hidden.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(pooled, want_p) and torch.equal(hidden, want_h)
