@@ -100,6 +100,26 @@ def test_text_path_with_fused_classifier_head(text_encoder):
 
 
 @pytest.mark.gpu
+def test_text_result_does_not_depend_on_workspace_contents(text_encoder):
+    """As for the speech path: a NaN-filled workspace changes nothing (slot padding rows are written before they are read)."""
+    import ctypes as C
+    toks = text_tokens(0)
+    nt = np.ascontiguousarray(np.asarray([len(t) for t in toks], dtype=np.int32))
+    packed = torch.from_numpy(np.concatenate(toks)).to(torch.int32).cuda()
+    want_p, want_h, info = text_encoder.encode_text_packed(packed, nt, return_hidden=True)
+    ws = torch.full((info["workspace_bytes"],), 0xFF, dtype=torch.uint8, device="cuda")
+    pooled = torch.empty(len(toks), 768, device="cuda")
+    hidden = torch.empty(info["total_frames"], 768, device="cuda")
+    with torch.cuda.device(text_encoder.device):
+        rc = text_encoder._lib.loco_encode_text(text_encoder._h, packed.data_ptr(), nt.ctypes.data, len(toks), pooled.data_ptr(),
+                                                hidden.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(pooled, want_p) and torch.equal(hidden, want_h)
+
+
+@pytest.mark.gpu
 def test_text_call_surface_and_errors(text_encoder, tsd):
     """encoder(input_ids) as the reference calls it (no mask: every position is a token), with a mask, and the errors."""
     from loco_asr_b200._lib import LocoError
