@@ -432,3 +432,22 @@ def test_result_does_not_depend_on_workspace_contents(encoder, fill):
     assert rc == 0
     torch.cuda.synchronize()
     assert torch.equal(pooled, want_p) and torch.equal(hidden, want_h)
+
+
+def test_long_segments_are_bit_identical_alone_and_in_a_mixed_batch(encoder):
+    """BASELINE.json configs[3] lengths (30 s -> 1499 frames, 60 s -> 2999 frames) next to a 1 s utterance: the long-context
+    attention path (both clamp regions of the bias table, 24-47 key blocks per query tile) gives the same bits for an
+    utterance alone and inside the mixed batch, and its frame count is the reference's."""
+    lengths = [960000, 16000, 480000]
+    wave = torch.randn(sum(lengths), device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)) * 0.1
+    pooled, hidden, info = encoder.encode_packed(wave, lengths, return_hidden=True)
+    assert info["frames"].tolist() == [2999, 49, 1499]
+    assert bool(torch.isfinite(hidden).all())
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    foffs = np.concatenate([[0], np.cumsum(info["frames"])])
+    for u in range(3):
+        p1, h1, _ = encoder.encode_packed(wave[int(offs[u]):int(offs[u + 1])].contiguous(), [lengths[u]], return_hidden=True)
+        assert torch.equal(p1[0], pooled[u]), u
+        assert torch.equal(h1, hidden[int(foffs[u]):int(foffs[u + 1])]), u
+    # unit-variance rows (SURVEY.md 8a15: the output of the last LayerNorm with gamma = 1, beta = 0)
+    assert abs(float(hidden.std(dim=1).mean()) - 1.0) < 2e-2
