@@ -12,6 +12,9 @@ Fixtures
                    70k SLURP-shaped set (lengths seed 1234, weights seed 1, waveform seed 1234): the HF module's pooled embedding
                    (stored fp16), and logits / argmax of IntentClassifier(average) with the seed-3 random Linear(768,101)
                    computed from the fp32 pooled vector.   ``python -m oracle.make_golden --config5-only``
+  long60_hf.npz    BASELINE.json configs[3]: one 60 s segment (T = 2999; the HF module materialises 2.3 GB of position_bias for it),
+                   weights seed 0, waveform seed 21: pooled, and 16 evenly spaced rows of last_hidden_state.
+                   ``python -m oracle.make_golden --long60-only``
   short_taps.npz   one 0.4 s noise utterance (T=19, all taps) and one 1.3 s utterance (T=64, three taps): stage-by-stage taps of the oracle
                    restatement *after* it has been checked against the HF module to 2e-5.
 """
@@ -86,6 +89,15 @@ def make_config5(out_dir):
                         margin=(top2[:, 0] - top2[:, 1]).numpy().astype(np.float32), weights_seed=1, wave_seed=1234, head_seed=3)
 
 
+def make_long60(out_dir):
+    model = build_hf_encoder(synth_state_dict(seed=0))
+    w = synth_wave(960000, 21, 7)
+    h = hf_encode_unpadded(model, [w])[0]
+    rows = np.linspace(0, h.shape[0] - 1, 16).astype(np.int64)
+    np.savez(os.path.join(out_dir, "long60_hf.npz"), n_samples=960000, wave_seed=21, wave_idx=7, n_frames=h.shape[0],
+             pooled=h.mean(0).numpy().astype(np.float32), rows=rows, hidden_rows=h[rows].numpy().astype(np.float32))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -93,6 +105,9 @@ def main():
     model = build_hf_encoder(sd)
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--long60-only" in sys.argv:
+        make_long60(out_dir)
+        return
     if "--config5-only" in sys.argv:
         make_config5(out_dir)
         return

@@ -451,3 +451,18 @@ def test_long_segments_are_bit_identical_alone_and_in_a_mixed_batch(encoder):
         assert torch.equal(h1, hidden[int(foffs[u]):int(foffs[u + 1])]), u
     # unit-variance rows (the output of the last LayerNorm with gamma = 1, beta = 0)
     assert abs(float(hidden.std(dim=1).mean()) - 1.0) < 2e-2
+
+
+def test_long_context_60s_against_golden_hf_vectors(encoder):
+    """BASELINE.json configs[3], 60 s (T = 2999): against tests/golden/long60_hf.npz, the unmodified HF module's pooled vector
+    and 16 evenly spaced rows of last_hidden_state (oracle/make_golden.py --long60-only; the module needs 2.3 GB of
+    position_bias for this one utterance)."""
+    g = np.load(os.path.join(GOLD, "long60_hf.npz"))
+    w = synth_wave(int(g["n_samples"]), int(g["wave_seed"]), int(g["wave_idx"]))
+    pooled, hidden, info = H.run_encoder(encoder, [w])
+    assert int(info["frames"][0]) == int(g["n_frames"]) == 2999
+    ref = torch.from_numpy(g["pooled"])
+    print(f"60 s: pooled cosine {H.cosine(pooled[0], ref):.6f}, rel err {H.rel_err(pooled[0], ref):.5f}")
+    assert H.cosine(pooled[0], ref) >= COS_MIN and H.rel_err(pooled[0], ref) < POOLED_REL_MAX
+    rows = torch.from_numpy(g["rows"])
+    assert H.rel_err(hidden[rows], torch.from_numpy(g["hidden_rows"])) < 5e-2
