@@ -105,3 +105,15 @@ def test_restatement_matches_config5_golden_subset():
         assert float((got - ref).abs().max() / ref.abs().max()) < 2e-3
         logit = torch.nn.functional.linear(got, *synth_head(3))
         assert float((logit - torch.from_numpy(g["logits"][i])).abs().max()) < 1e-3
+
+
+def test_restatement_matches_hf_on_a_60s_segment():
+    """T = 2999: both clamp regions of the relative-position table are in play.  The restatement's table form
+    (q . pe_k^T, gathered) against the HF module's [T, T, 64] contraction, as stored in tests/golden/long60_hf.npz."""
+    g = np.load(os.path.join(GOLD, "long60_hf.npz"))
+    w = synth_wave(int(g["n_samples"]), int(g["wave_seed"]), int(g["wave_idx"]))
+    h = O.encode_utterance(synth_state_dict(seed=0), torch.from_numpy(w))
+    assert h.shape[0] == int(g["n_frames"]) == 2999
+    ref = torch.from_numpy(g["pooled"])
+    assert float((h.mean(0) - ref).abs().max() / ref.abs().max()) < 5e-5
+    assert float((h[torch.from_numpy(g["rows"])] - torch.from_numpy(g["hidden_rows"])).abs().max()) < 5e-4
