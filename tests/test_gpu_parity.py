@@ -466,3 +466,15 @@ def test_long_context_60s_against_golden_hf_vectors(encoder):
     assert H.cosine(pooled[0], ref) >= COS_MIN and H.rel_err(pooled[0], ref) < POOLED_REL_MAX
     rows = torch.from_numpy(g["rows"])
     assert H.rel_err(hidden[rows], torch.from_numpy(g["hidden_rows"])) < 5e-2
+
+
+def test_utterance_longer_than_max_speech_positions(encoder, weights):
+    """90 s -> 4499 frames, past config.max_speech_positions = 4000: HF grows its sinusoid table on demand
+    (HF:331-333) and so does the library (loco_encode rebuilds the device table); checked against the oracle."""
+    w = synth_wave(1440000, 31, 0)
+    pooled, hidden, info = H.run_encoder(encoder, [w])
+    assert int(info["frames"][0]) == 4499
+    ref = O.encode_utterance(weights, torch.from_numpy(w))
+    assert H.cosine(pooled[0], ref.mean(0)) >= COS_MIN
+    assert H.rel_err(hidden[4000:], ref[4000:]) < 5e-2        # the frames whose positions lie beyond the initial table
+    assert H.rel_err(hidden, ref) < 5e-2
