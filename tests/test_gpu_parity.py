@@ -478,3 +478,18 @@ def test_utterance_longer_than_max_speech_positions(encoder, weights):
     assert H.cosine(pooled[0], ref.mean(0)) >= COS_MIN
     assert H.rel_err(hidden[4000:], ref[4000:]) < 5e-2        # the frames whose positions lie beyond the initial table
     assert H.rel_err(hidden, ref) < 5e-2
+
+
+def test_twenty_thousand_tiny_utterances_in_one_launch(encoder):
+    """The other extreme of the batch shape: 20000 utterances of 1-3 frames (25-75 ms) in one launch -- per-utterance grids,
+    work lists and metadata at their widest; spot-checked bit-identical against single-utterance encodes."""
+    rng = np.random.default_rng(3)
+    lengths = rng.integers(400, 1200, size=20000).tolist()
+    wave = torch.randn(int(np.sum(lengths)), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * 0.1
+    pooled, hidden, info = encoder.encode_packed(wave, lengths, return_hidden=True)
+    assert bool(torch.isfinite(pooled).all())
+    assert info["frames"].tolist() == [(n - 400) // 320 + 1 for n in lengths]
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    for u in (0, 1, 9999, 19998, 19999):
+        alone = encoder.encode_packed(wave[int(offs[u]):int(offs[u + 1])].contiguous(), [lengths[u]])
+        assert torch.equal(alone[0], pooled[u]), u
