@@ -197,11 +197,8 @@ class LocoSpeechT5Encoder:
         self._head_method = method
 
     def _head_outputs(self, n: int, with_head: bool):
-        """Allocate the head's outputs for one encode call and point the library at them (or switch the head off)."""
+        """Allocate the head's outputs for one encode call and point the library at them."""
         if not with_head:
-            if getattr(self, "_head_on", False):
-                _lib.check(self._lib, self._h, self._lib.loco_set_head_outputs(self._h, None, None), "loco_set_head_outputs")
-                self._head_on = False
             return None, None
         if getattr(self, "_head_method", None) is None:
             raise _lib.LocoError("with_head=True before set_head()")
@@ -209,8 +206,12 @@ class LocoSpeechT5Encoder:
         lg = torch.empty(n, self._head_classes, dtype=torch.float32, device=self.device) if self._head_classes else None
         rc = self._lib.loco_set_head_outputs(self._h, hp.data_ptr(), lg.data_ptr() if lg is not None else None)
         _lib.check(self._lib, self._h, rc, "loco_set_head_outputs")
-        self._head_on = True
         return hp, lg
+
+    def _head_outputs_off(self, with_head: bool):
+        """The launch has captured the pointers; no later call (e.g. ``encode_host``) may write through them again."""
+        if with_head:
+            _lib.check(self._lib, self._h, self._lib.loco_set_head_outputs(self._h, None, None), "loco_set_head_outputs")
 
     def encode_packed(self, wave: torch.Tensor, n_samples: Sequence[int], return_hidden: bool = False,
                       out: Optional[torch.Tensor] = None, with_head: bool = False):
@@ -235,6 +236,7 @@ class LocoSpeechT5Encoder:
             rc = self._lib.loco_encode(self._h, wave.data_ptr(), ns.ctypes.data, n, pooled.data_ptr(),
                                        hidden.data_ptr() if hidden is not None else None, ws.data_ptr(),
                                        ws.numel(), C.c_void_p(stream))
+        self._head_outputs_off(with_head)
         _lib.check(self._lib, self._h, rc, "loco_encode")
         self._last_plan = info
         if with_head:
@@ -343,6 +345,7 @@ class LocoSpeechT5Encoder:
             rc = self._lib.loco_encode_text(self._h, tokens.data_ptr(), nt.ctypes.data, n, pooled.data_ptr(),
                                             hidden.data_ptr() if hidden is not None else None, ws.data_ptr(), ws.numel(),
                                             C.c_void_p(stream))
+        self._head_outputs_off(with_head)
         _lib.check(self._lib, self._h, rc, "loco_encode_text")
         info = {"frames": nt.copy(), "rows": rows, "total_frames": int(total.value), "workspace_bytes": int(wsb.value)}
         self._last_plan = info

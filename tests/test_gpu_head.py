@@ -62,9 +62,14 @@ def test_fused_head_equals_reference_forward_on_the_returned_hidden_states(encod
         assert torch.allclose(lg[u], ref_l, rtol=0, atol=1e-4 * max(1.0, float(ref_l.abs().max()))), (u, t)
         assert int(lg[u].argmax()) == int(ref_l.argmax())
         off += t
-    # the head switched off again: the plain call returns only the masked mean, identical bits
+    # the head is off again after the call: a plain call (and the host-buffer path, which never sees the head's tensors)
+    # returns only the masked mean, identical bits, and leaves the earlier head outputs alone
+    keep_hp, keep_lg = info["head_pooled"].clone(), info["logits"].clone()
     again = encoder.encode_packed(wave, [len(x) for x in waves]).cpu()
     assert torch.equal(again, pooled)
+    host = encoder.encode_host(wave.cpu().pin_memory(), [len(x) for x in waves])
+    assert torch.equal(host, pooled)
+    assert torch.equal(info["head_pooled"], keep_hp) and torch.equal(info["logits"], keep_lg)
 
 
 @pytest.mark.parametrize("method", ["max", "attention"])
