@@ -235,6 +235,16 @@ def main():
     prof = enc.profile_collect()
     enc.profile_enable(False)
     launches = enc.launch_count - launches0
+    # ---- the timed outputs themselves (untimed check): every pooled embedding finite, and three of the timed batches
+    # re-encoded give the same bits (the path is deterministic, so a checksum of the timed pass is reproducible)
+    timed_rows = torch.cat([torch.arange(row0[b], row0[b] + len(lens[b]), device=dev) for b in sorted(set(steps[W:]))])
+    out_finite = bool(torch.isfinite(pooled_all[timed_rows]).all())
+    checksum = float(pooled_all[timed_rows].double().sum())
+    recheck = sorted(set(steps[W:]))
+    recheck = [recheck[0], recheck[len(recheck) // 2], recheck[-1]]
+    out_repro = all(torch.equal(enc.encode_packed(waves[b], lens[b]), pooled_all[row0[b]:row0[b] + len(lens[b])]) for b in recheck)
+    outputs = {"utterances": int(timed_rows.numel()), "all_finite": out_finite, "bit_reproducible": out_repro,
+               "rechecked_batches": len(set(recheck)), "pooled_checksum": checksum}
     timed_audio = sum(audio_s[b] for b in steps[W:])
     t = torch.tensor([ms, timed_audio], dtype=torch.float64, device=dev)
     if world > 1:
@@ -352,7 +362,7 @@ def main():
                        "l2": "inputs larger than L2 (per-step working set ~20 GB)",
                        "parallelism": f"dp{world} utterance-sharded, one all-gather of pooled embeddings"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "stage_ms_per_step": stage_ms, "whole_step": whole, "parity": parity,
+            "clocks": clocks, "stage_ms_per_step": stage_ms, "whole_step": whole, "parity": parity, "outputs": outputs,
         }))
     if world > 1:
         dist.destroy_process_group()
