@@ -102,7 +102,11 @@ LOCO_API int loco_finalize_weights(loco_handle* h);
  *   frames[n_utts]   encoder frames T_u per utterance (HF _get_feat_extract_output_lengths, :585-598)
  *   rows[n_utts]     first row of utterance u in the slot-packed [R6, *] stage buffers (debug taps)
  *   total_frames     sum of T_u  (rows of the compact hidden_out)
- *   workspace_bytes  device scratch loco_encode needs for this batch */
+ *   workspace_bytes  device scratch loco_encode needs for this batch.  The workspace pointer may have ANY alignment
+ *                    (cudaMalloc: 256 B, torch's caching allocator: 512 B): the figure includes 1024 bytes of slack and
+ *                    loco_encode / loco_encode_text / loco_encode_host round the base up to the 1024-byte boundary the
+ *                    TMA boxes and swizzled tiles inside want.
+ * At most 65535 utterances per call (LOCO_ERR_INVALID beyond); split larger sets into several calls. */
 LOCO_API int loco_plan(loco_handle* h, const int32_t* n_samples, int n_utts, int32_t* frames, int32_t* rows,
               int64_t* total_frames, size_t* workspace_bytes);
 
@@ -111,6 +115,7 @@ LOCO_API int loco_plan(loco_handle* h, const int32_t* n_samples, int n_utts, int
  *   n_samples     i32[n_utts]         (host)
  *   pooled_dev    f32[n_utts, 768]    mean of last_hidden_state over each utterance's own frames (device)
  *   hidden_dev    f32[total_frames, 768] or NULL: last_hidden_state, utterances concatenated (device)
+ *   workspace_dev any alignment, at least loco_plan's workspace_bytes (LOCO_ERR_WORKSPACE otherwise); wave_dev 4-byte aligned
  * Asynchronous on `stream`. */
 LOCO_API int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples, int n_utts, float* pooled_dev,
                 float* hidden_dev, void* workspace_dev, size_t workspace_bytes, void* stream);

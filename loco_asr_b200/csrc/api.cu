@@ -130,6 +130,19 @@ int fail(loco_handle* h, int code, const std::string& msg) {
 
 size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
 
+// The stage buffers inside the workspace want 1024-byte alignment (TMA boxes, SWIZZLE_128B atoms).  The caller's pointer
+// may have any alignment (cudaMalloc promises 256 B, torch's caching allocator 512 B): loco_plan* report kWsSlack bytes more
+// than the layout needs and the encode calls round the base up themselves.
+constexpr size_t kWsSlack = 1024;
+constexpr int kMaxUtts = 65535;     // utterances per call: the per-utterance kernels index them with gridDim.y / gridDim.x
+bool carve_workspace(void* base, size_t bytes, size_t need, uint8_t** aligned) {
+    const uintptr_t b = reinterpret_cast<uintptr_t>(base);
+    const uintptr_t a = (b + 1023) & ~(uintptr_t)1023;
+    const size_t lost = (size_t)(a - b);
+    *aligned = reinterpret_cast<uint8_t*>(a);
+    return bytes >= lost && bytes - lost >= need;
+}
+
 std::string canon_key(const char* key) {
     std::string k(key);
     const char* pres[] = {"speecht5.encoder.", "encoder."};
@@ -262,6 +275,7 @@ int build_text_pe(loco_handle* h, int rows) {
 
 // Geometry of a text batch: a row is a token, utterances back to back (no slot padding), only the transformer buffers.
 int make_layout_text(loco_handle* h, const int32_t* n_tokens, int n_utts, Layout* L) {
+    if (n_utts < 0 || n_utts > kMaxUtts) return fail(h, LOCO_ERR_INVALID, "n_utts must be in [0, " + std::to_string(kMaxUtts) + "]");
     L->n_utts = n_utts;
     L->meta.resize(n_utts);
     int64_t row = 0;
@@ -316,7 +330,7 @@ int make_layout_text(loco_handle* h, const int32_t* n_tokens, int n_utts, Layout
 }
 
 int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L) {
-    if (n_utts < 0 || n_utts > 65535) return fail(h, LOCO_ERR_INVALID, "n_utts must be in [0, 65535]");
+    if (n_utts < 0 || n_utts > kMaxUtts) return fail(h, LOCO_ERR_INVALID, "n_utts must be in [0, " + std::to_string(kMaxUtts) + "]");
     L->n_utts = n_utts;
     L->meta.resize(n_utts);
     int64_t row = 0, out_row = 0, off = 0;
@@ -508,7 +522,7 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
     chk(cfg->activation_is_gelu == 1, "activation");
     chk(cfg->conv_bias == 0, "conv_bias");
     chk(fabsf(cfg->layer_norm_eps - 1e-5f) < 1e-9f, "layer_norm_eps");
-    chk(cfg->pad_token_id >= 0, "pad_token_id");
+    chk(cfg->pad_token_id == 1, "pad_token_id (the sinusoid position of frame t is t + pad_token_id + 1 = t + 2, HF:349-351)");
     if (!bad.empty()) {
         g_create_error = "unsupported SpeechT5 encoder config (kernels are built for the SpeechT5-base shape family): " + bad;
         return LOCO_ERR_INVALID;
@@ -880,7 +894,7 @@ int loco_plan(loco_handle* h, const int32_t* n_samples, int n_utts, int32_t* fra
         if (rows) rows[u] = L.meta[u].row6;
     }
     if (total_frames) *total_frames = L.total_frames;
-    if (workspace_bytes) *workspace_bytes = L.bytes;
+    if (workspace_bytes) *workspace_bytes = L.bytes + kWsSlack;
     return LOCO_OK;
 }
 
@@ -891,23 +905,23 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
     if (!h->has_speech) return fail(h, LOCO_ERR_STATE, "loco_encode: this handle was loaded without the speech prenet (text-only weights)");
     if (n_utts == 0) return LOCO_OK;
     if (!wave_dev || !n_samples || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode: null argument");
-    if ((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) != 0) return fail(h, LOCO_ERR_INVALID, "workspace must be 1024-byte aligned");
     if ((reinterpret_cast<uintptr_t>(wave_dev) & 3) != 0) return fail(h, LOCO_ERR_INVALID, "wave_dev must be 4-byte aligned");
     prof_break(h);
     Layout& L = h->last;
     L = Layout();
     int rc = make_layout(h, n_samples, n_utts, &L);
     if (rc) return rc;
-    if (workspace_bytes < L.bytes)
-        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes) + " bytes, got " + std::to_string(workspace_bytes));
+    uint8_t* ws = nullptr;
+    if (!carve_workspace(workspace_dev, workspace_bytes, L.bytes, &ws))
+        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes + kWsSlack) +
+                                               " bytes (loco_plan's workspace_bytes), got " + std::to_string(workspace_bytes));
     CK(cudaSetDevice(h->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (L.max_t6 + h->cfg.pad_token_id + 1 >= h->sin_rows) {  // HF grows its table on demand too (HF:331-333)
         CK(cudaStreamSynchronize(s));
         if ((rc = build_sin_table(h, L.max_t6 + h->cfg.pad_token_id + 1024))) return rc;
     }
-    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
-    h->last_ws = workspace_dev;
+    h->last_ws = ws;
     auto B = [&](const char* name) { return reinterpret_cast<bf16*>(ws + L.bufs[name].off); };
     UttMeta* meta = reinterpret_cast<UttMeta*>(ws + L.off_meta);
     double* partial = reinterpret_cast<double*>(ws + L.off_partial);
@@ -971,7 +985,7 @@ int loco_host_workspace_bytes(loco_handle* h, const int32_t* n_samples, int n_ut
     Layout L;
     int rc = make_layout(h, n_samples, n_utts, &L);
     if (rc) return rc;
-    *bytes = L.bytes + align_up((size_t)L.total_samples * sizeof(float)) + align_up((size_t)n_utts * kHidden * sizeof(float)) +
+    *bytes = kWsSlack + L.bytes + align_up((size_t)L.total_samples * sizeof(float)) + align_up((size_t)n_utts * kHidden * sizeof(float)) +
              (want_hidden ? align_up((size_t)L.total_frames * kHidden * sizeof(float)) : 0);
     return LOCO_OK;
 }
@@ -988,16 +1002,17 @@ int loco_encode_host(loco_handle* h, const float* wave_host, const int32_t* n_sa
     const size_t pooled_bytes = (size_t)n_utts * kHidden * sizeof(float);
     const size_t hidden_bytes = hidden_host ? (size_t)L.total_frames * kHidden * sizeof(float) : 0;
     const size_t need = L.bytes + align_up(wave_bytes) + align_up(pooled_bytes) + align_up(hidden_bytes);
-    if (workspace_bytes < need)
-        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small for host encode: need " + std::to_string(need) + " bytes, got " + std::to_string(workspace_bytes));
+    uint8_t* ws = nullptr;
+    if (!carve_workspace(workspace_dev, workspace_bytes, need, &ws))
+        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small for host encode: need " + std::to_string(need + kWsSlack) +
+                                               " bytes (loco_host_workspace_bytes), got " + std::to_string(workspace_bytes));
     CK(cudaSetDevice(h->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
     float* wave_dev = reinterpret_cast<float*>(ws + L.bytes);
     float* pooled_dev = reinterpret_cast<float*>(ws + L.bytes + align_up(wave_bytes));
     float* hidden_dev = hidden_host ? reinterpret_cast<float*>(ws + L.bytes + align_up(wave_bytes) + align_up(pooled_bytes)) : nullptr;
     CK(cudaMemcpyAsync(wave_dev, wave_host, wave_bytes, cudaMemcpyHostToDevice, s));
-    rc = loco_encode(h, wave_dev, n_samples, n_utts, pooled_dev, hidden_dev, workspace_dev, L.bytes, stream);
+    rc = loco_encode(h, wave_dev, n_samples, n_utts, pooled_dev, hidden_dev, ws, L.bytes, stream);
     if (rc) return rc;
     CK(cudaMemcpyAsync(pooled_host, pooled_dev, pooled_bytes, cudaMemcpyDeviceToHost, s));
     if (hidden_host) CK(cudaMemcpyAsync(hidden_host, hidden_dev, hidden_bytes, cudaMemcpyDeviceToHost, s));
@@ -1013,7 +1028,7 @@ int loco_plan_text(loco_handle* h, const int32_t* n_tokens, int n_utts, int32_t*
     for (int u = 0; u < n_utts; ++u)
         if (rows) rows[u] = L.meta[u].row6;
     if (total_tokens) *total_tokens = L.total_frames;
-    if (workspace_bytes) *workspace_bytes = L.bytes;
+    if (workspace_bytes) *workspace_bytes = L.bytes + kWsSlack;
     return LOCO_OK;
 }
 
@@ -1024,22 +1039,22 @@ int loco_encode_text(loco_handle* h, const int32_t* tokens_dev, const int32_t* n
     if (!h->has_text) return fail(h, LOCO_ERR_STATE, "loco_encode_text: this handle was loaded without the text prenet (prenet.embed_tokens.weight)");
     if (n_utts == 0) return LOCO_OK;
     if (!tokens_dev || !n_tokens || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode_text: null argument");
-    if ((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) != 0) return fail(h, LOCO_ERR_INVALID, "workspace must be 1024-byte aligned");
     prof_break(h);
     Layout& L = h->last;
     L = Layout();
     int rc = make_layout_text(h, n_tokens, n_utts, &L);
     if (rc) return rc;
-    if (workspace_bytes < L.bytes)
-        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes) + " bytes, got " + std::to_string(workspace_bytes));
+    uint8_t* ws = nullptr;
+    if (!carve_workspace(workspace_dev, workspace_bytes, L.bytes, &ws))
+        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes + kWsSlack) +
+                                               " bytes (loco_plan_text's workspace_bytes), got " + std::to_string(workspace_bytes));
     CK(cudaSetDevice(h->device));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (L.max_t6 > h->txt_pe_rows) {      // HF's table stops at max_text_positions (450); this one grows on demand
         CK(cudaStreamSynchronize(s));
         if ((rc = build_text_pe(h, L.max_t6 + 1024))) return rc;
     }
-    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
-    h->last_ws = workspace_dev;
+    h->last_ws = ws;
     UttMeta* meta = reinterpret_cast<UttMeta*>(ws + L.off_meta);
     int32_t* row_frame = reinterpret_cast<int32_t*>(ws + L.off_rowframe);
     CK(cudaMemcpyAsync(meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta), cudaMemcpyHostToDevice, s));

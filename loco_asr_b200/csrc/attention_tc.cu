@@ -123,8 +123,9 @@ __device__ __forceinline__ uint32_t idesc_rt(int n) {      // M = 128, runtime N
 }
 
 // Bounded spin without the printf of common.cuh's mbar_wait (the call would cost this kernel registers and spills).
-// A protocol bug does not hang the GPU: the first wait that runs out records (tag, block, thread, parity) in g_fa_timeout
-// and execution continues with garbage; launch_attention_tc reports it when LOCO_ATTN_DEBUG is set.
+// A protocol bug does not hang the GPU and never returns garbage: the first wait that runs out records (tag, block, thread,
+// parity) in g_fa_timeout and TRAPS, so the launch fails and the next CUDA call of loco_encode / the caller's synchronise
+// reports it (LOCO_ERR_CUDA); launch_attention_tc prints the record when LOCO_ATTN_DEBUG is set.
 __device__ int g_fa_timeout[4 * 4 + 1];      // [role][tag + 1, block, thread, parity], then a "someone timed out" flag
 __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
     uint32_t spins = 0;
@@ -140,7 +141,8 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity, int tag 
                 g_fa_timeout[role * 4 + 2] = (int)threadIdx.x;
                 g_fa_timeout[role * 4 + 3] = (int)parity;
             }
-            return;
+            __threadfence();
+            __trap();
         }
 }
 
@@ -529,7 +531,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             if (active || prev_active) named_bar_sync(bar_id, 64);   // the other group is done with the previous item's table rows
                                                                       // and has published its maxima / sums
             const int n_chunks = (it.nc16 + 31) >> 5;
+            // Only the table columns this warp's 32 rows can reach are drained: rel = i - j for its rows i and the keys j of the
+            // utterance, clamped -- a window of T + 31 columns out of the tile's T + 127.
+            const int w_lo = max(it.i0 + q * 32 - (it.T - 1), -kMaxRel) + kMaxRel - it.cbase;
+            const int w_hi = min(it.i0 + q * 32 + 31, kMaxRel - 1) + kMaxRel - it.cbase;
+            const int c_first = w_lo >> 5, c_last = min(w_hi >> 5, n_chunks - 1);
             auto drain = [&](int c, int tcol) {
+                if (c < c_first || c > c_last) return;
                 uint32_t v[32];
                 tmem_ld_32x32(t_lane + TM_G + tcol, v);
                 tmem_ld_wait(v);

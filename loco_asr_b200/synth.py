@@ -88,6 +88,56 @@ def synth_waves_device(lengths: Sequence[int], seed: int, device, chunk: int = 2
     return out
 
 
+def _mix64(x: "torch.Tensor") -> "torch.Tensor":
+    """splitmix64 finaliser on int64 tensors (wrapping arithmetic; logical shifts emulated with masks)."""
+    x = (x ^ ((x >> 30) & 0x3FFFFFFFF)) * -4658895280553007687          # 0xBF58476D1CE4E5B9
+    x = (x ^ ((x >> 27) & 0x1FFFFFFFFF)) * -7723592293110705685         # 0x94D049BB133111EB
+    return x ^ ((x >> 31) & 0x1FFFFFFFF)
+
+
+def _uniform01(h: "torch.Tensor", shift: int = 0) -> "torch.Tensor":
+    """24 bits of a hash -> float32 in (0, 1)."""
+    return (((h >> shift) & 0xFFFFFF).to(torch.float32) + 0.5) * (1.0 / 16777216.0)
+
+
+def synth_waves_by_id(lengths: Sequence[int], ids: Sequence[int], seed: int, device, max_elems: int = 1 << 26) -> "torch.Tensor":
+    """Packed float32 waveforms [sum(lengths)] on `device`, utterance u a pure function of (seed, ids[u], lengths[u]):
+    the same utterance gets the same samples whatever batch, rank or order it is generated in -- what lets a sharded
+    multi-GPU pass be compared bit for bit with the single-GPU pass.  Same recipe as :func:`synth_wave` (amplitude-modulated
+    5-tone mixture + 0.005 N(0,1)), counter-based random numbers (splitmix64 of (seed, id, sample index))."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    ids_t = torch.as_tensor(np.asarray(ids, dtype=np.int64), device=device)
+    total = int(lengths.sum())
+    out = torch.empty(total, dtype=torch.float32, device=device)
+    cu = np.concatenate([[0], np.cumsum(lengths)])
+    base = _mix64(ids_t * -7046029254386353131 + int(seed))              # 0x9E3779B97F4A7C15: one stream per (seed, id)
+    s = 0
+    n_all = len(lengths)
+    while s < n_all:
+        e, lmax = s + 1, int(lengths[s])
+        while e < n_all and max(lmax, int(lengths[e])) * (e - s + 1) <= max_elems:
+            lmax = max(lmax, int(lengths[e]))
+            e += 1
+        n = e - s
+        b = base[s:e, None]
+        par = _mix64(b + torch.arange(1, 17, device=device, dtype=torch.int64)[None, :] * 6364136223846793005)
+        u = _uniform01(par)                                               # [n, 16] utterance parameters
+        f, a, ph, fe = u[:, 0:5] * 3000.0 + 80.0, u[:, 5:10], u[:, 10:15] * (2 * math.pi), u[:, 15:16] * 2.0 + 0.5
+        t = torch.arange(lmax, device=device, dtype=torch.float32)[None, :] / SAMPLE_RATE
+        x = torch.zeros(n, lmax, device=device)
+        for m in range(5):
+            x += a[:, m:m + 1] * torch.sin(2 * math.pi * f[:, m:m + 1] * t + ph[:, m:m + 1])
+        x = 0.1 * torch.sin(2 * math.pi * fe * t) ** 2 * x
+        h = _mix64(b ^ (torch.arange(lmax, device=device, dtype=torch.int64)[None, :] * -3335678366873096957 + 0x5851F42D))
+        x += 0.005 * torch.sqrt(-2.0 * torch.log(_uniform01(h))) * torch.cos((2 * math.pi) * _uniform01(h, 24))
+        del h
+        mask = torch.arange(lmax, device=device)[None, :] < torch.as_tensor(lengths[s:e], device=device)[:, None]
+        out[int(cu[s]):int(cu[e])] = x[mask]
+        del x, mask
+        s = e
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # weights
 # ----------------------------------------------------------------------------------------------

@@ -434,6 +434,35 @@ def test_result_does_not_depend_on_workspace_contents(encoder, fill):
     assert torch.equal(pooled, want_p) and torch.equal(hidden, want_h)
 
 
+@pytest.mark.parametrize("misalign", [4, 256, 1000])
+def test_workspace_may_have_any_alignment(encoder, misalign):
+    """The C ABI takes the caller's workspace pointer as it is (cudaMalloc promises 256 B, torch's allocator 512 B): the library
+    rounds the base up itself and loco_plan's workspace_bytes already includes the slack.  Same bits whatever the offset."""
+    import ctypes as C
+    lengths = [400, 12000, 41200, 64000, 7777]
+    ns = np.ascontiguousarray(np.asarray(lengths, dtype=np.int32))
+    n = len(lengths)
+    info = encoder.plan(ns)
+    wave = torch.randn(int(ns.sum()), device="cuda", generator=torch.Generator(device="cuda").manual_seed(6)) * 0.1
+    want = encoder.encode_packed(wave, lengths)
+    raw = torch.empty(info["workspace_bytes"] + 2048, dtype=torch.uint8, device="cuda")
+    off = (-raw.data_ptr()) % 1024 + misalign              # base is exactly `misalign` bytes past a 1024-byte boundary
+    ws = raw[off:off + info["workspace_bytes"]]
+    assert ws.data_ptr() % 1024 == misalign % 1024
+    pooled = torch.empty(n, 768, device="cuda")
+    with torch.cuda.device(encoder.device):
+        rc = encoder._lib.loco_encode(encoder._h, wave.data_ptr(), ns.ctypes.data, n, pooled.data_ptr(), None,
+                                      ws.data_ptr(), ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, encoder._lib.loco_last_error(encoder._h)
+    torch.cuda.synchronize()
+    assert torch.equal(pooled, want)
+    # one byte less than loco_plan asked for is refused with the workspace error, never written past
+    with torch.cuda.device(encoder.device):
+        rc = encoder._lib.loco_encode(encoder._h, wave.data_ptr(), ns.ctypes.data, n, pooled.data_ptr(), None,
+                                      ws.data_ptr(), ws.numel() - 1025, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == -4
+
+
 def test_long_segments_are_bit_identical_alone_and_in_a_mixed_batch(encoder):
     """BASELINE.json configs[3] lengths (30 s -> 1499 frames, 60 s -> 2999 frames) next to a 1 s utterance: the long-context
     attention path (both clamp regions of the bias table, 24-47 key blocks per query tile) gives the same bits for an
