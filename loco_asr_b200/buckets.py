@@ -74,6 +74,15 @@ def shard_batches(costs: Sequence[float], world_size: int) -> List[List[int]]:
     return out
 
 
+def shard_utterances(lengths: Sequence[int], world_size: int) -> List[np.ndarray]:
+    """Utterance-level sharding for one box of `world_size` GPUs: sort by length (stable) and deal the sorted list
+    round-robin, so every rank gets the same length distribution -- hence the same FLOPs to within one utterance per
+    length class and the same batch shapes -- and every rank can derive every other rank's share from the lengths alone
+    (no ids travel).  Returns, per rank, the POSITIONS into `lengths` it owns, shortest first."""
+    order = np.argsort(np.asarray(lengths, dtype=np.int64), kind="stable")
+    return [order[r::world_size] for r in range(world_size)]
+
+
 def interleaved_order(n: int) -> List[int]:
     """Visit 0..n-1 with a stride coprime to n so that any prefix is a representative mix of lengths."""
     if n <= 2:

@@ -60,3 +60,16 @@ def test_single_process_gather_is_a_scatter():
     ids = np.array([3, 0, 2, 1])
     out = gather_pooled(_fake_pooled(ids), ids, [4], 4)
     assert torch.equal(out, _fake_pooled(np.arange(4)))
+
+
+def test_shard_utterances_is_a_balanced_partition():
+    from loco_asr_b200.buckets import shard_utterances
+    from loco_asr_b200.flops import total_flops
+    lengths = slurp_shaped_lengths(20000, 5)
+    for world in (1, 2, 4, 8):
+        shards = shard_utterances(lengths, world)
+        assert sorted(np.concatenate(shards).tolist()) == list(range(len(lengths)))          # every utterance exactly once
+        assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+        assert all(np.all(np.diff(lengths[s]) >= 0) for s in shards)                         # shortest first: dense batches
+        fl = [total_flops(lengths[s]) for s in shards]
+        assert max(fl) / (sum(fl) / world) < 1.002                                           # FLOP-balanced to 0.2 %
