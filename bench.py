@@ -202,7 +202,8 @@ def main():
     import torch.distributed as dist
 
     strong = args.scaling == "strong"
-    enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device=dev)
+    dbg = args.attn_impl >= 0 or args.gemm_impl >= 0 or args.ln_impl >= 0       # kernel switches exist only in the LOCO_DEBUG build
+    enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device=dev, debug=dbg)
     if args.attn_impl >= 0:
         enc.debug_set("attn_impl", args.attn_impl)
     if args.gemm_impl >= 0:

@@ -15,8 +15,10 @@
  *     Nothing throws, nothing calls exit().
  *   - OWNERSHIP: the caller owns every device buffer it passes in (waveforms, outputs, workspace) -- the
  *     Python host allocates them through torch's caching allocator.  The handle owns only its weight copies.
- *   - STREAMS: all work is enqueued on the caller's stream (a cudaStream_t passed as void*); the only host
- *     synchronisation is inside loco_encode_host (which must hand host memory back).
+ *   - STREAMS: all work is enqueued on the caller's stream (a cudaStream_t passed as void*).  Host synchronisation happens
+ *     only in loco_encode_host (which must hand host memory back), in loco_sync_check, and the FIRST time loco_encode /
+ *     loco_encode_text see a batch geometry (they build and cache its plan; see loco_plan_create).  Asynchronous CUDA errors
+ *     surface at the next call or at loco_sync_check.
  *   - a handle is bound to one device, is not thread-safe; use one handle per rank.
  */
 #ifndef LOCO_ASR_H_
@@ -29,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LOCO_ABI_VERSION 1
+#define LOCO_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define LOCO_API __attribute__((visibility("default")))
@@ -120,6 +122,25 @@ LOCO_API int loco_plan(loco_handle* h, const int32_t* n_samples, int n_utts, int
 LOCO_API int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples, int n_utts, float* pooled_dev,
                 float* hidden_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- plans: a batch geometry made ready to launch --------------------------------------------------------------------
+ * loco_plan_create computes the layout and the kernels' work lists for one batch (kind 0: speech, lengths = samples per
+ * utterance; kind 1: text, lengths = tokens per text) and uploads them into a small device block owned by the plan.  It is
+ * synchronous (cudaMalloc + cudaMemcpy): call it outside hot loops and outside stream captures.
+ * loco_encode_planned is then a pure enqueue on `stream` -- kernels and memset nodes only, no host-to-device copy, no host
+ * synchronisation -- so it may be captured into a CUDA graph: capture one call per bucket, then replay the graph after
+ * refilling the same input buffer (same lengths).  The caller still owns input, outputs and workspace (loco_plan_info's
+ * workspace_bytes; any alignment).  A plan may be used any number of times, from one handle, until loco_plan_destroy.
+ * loco_encode / loco_encode_text are exactly loco_plan_create (cached per geometry, up to 256 of them) + loco_encode_planned. */
+typedef struct loco_batch_plan loco_batch_plan;
+LOCO_API int loco_plan_create(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loco_batch_plan** out);
+LOCO_API int loco_plan_info(const loco_batch_plan* plan, int32_t* frames, int32_t* rows, int64_t* total_frames, size_t* workspace_bytes);
+LOCO_API int loco_encode_planned(loco_handle* h, const loco_batch_plan* plan, const void* input_dev /* f32 waveforms | i32 tokens */,
+                                 float* pooled_dev, float* hidden_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+LOCO_API void loco_plan_destroy(loco_handle* h, loco_batch_plan* plan);
+
+/* Synchronise `stream` and report any asynchronous CUDA error of the work enqueued so far (LOCO_ERR_CUDA + message). */
+LOCO_API int loco_sync_check(loco_handle* h, void* stream);
+
 /* Same call with HOST buffers: copies the waveforms H2D (staged in the tail of the workspace), encodes,
  * copies pooled (and hidden) D2H and synchronises `stream` before returning.  The workspace must be
  * loco_host_workspace_bytes() large.  This is the path bench.py's `e2e` number times. */
@@ -174,7 +195,11 @@ LOCO_API int64_t loco_launch_count(const loco_handle* h);
 LOCO_API int loco_profile_enable(loco_handle* h, int on);
 LOCO_API int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_t* launches);
 
-/* ---- debug / test hooks (not part of the product surface) ------------------------------------------- */
+/* ---- debug / test hooks (not part of the product surface) -------------------------------------------
+ * The product library (libloco_asr.so) contains only the product kernels; loco_debug_set fails on it.  The cross-check
+ * kernels (SIMT GEMM, single-CTA tcgen05 GEMM, mma.sync positional conv and attention, stand-alone LayerNorm path) and the
+ * knobs that select them are compiled only with -DLOCO_DEBUG into libloco_asr_debug.so, which the unit tests load. */
+LOCO_API int loco_is_debug_build(void);
 /* name: "gemm_impl" (2 = tcgen05 CTA pair, cta_group::2 [default], 0 = tcgen05 single CTA, 1 = SIMT reference), "posconv_impl" (0 = tcgen05 [default],
  * 1 = mma.sync cross-check), "ln_impl" (0 = the transformer layers' LayerNorms deferred into the GEMM epilogues [default, needs gemm_impl 2],
  * 1 = LayerNorm kernels), "attn_impl" (-1 = per utterance by its own frame count [default], 0 = tcgen05, 1 = mma.sync), "attn_tc_min_frames" / "attn_tc_lo" / "attn_tc_hi" (the frame ranges that select the tcgen05 kernel), "stop_after_layer"

@@ -11,6 +11,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LOCO_ASR_LIB") or os.path.join(_HERE, "libloco_asr.so")   # env override: A/B builds in tools/
+DEBUG_LIB_PATH = os.path.join(_HERE, "libloco_asr_debug.so")     # -DLOCO_DEBUG: product kernels + cross-check kernels + knobs (tests)
+ABI_VERSION = 2
 CSRC = os.path.join(_HERE, "csrc")
 
 LOCO_F32, LOCO_F16, LOCO_BF16, LOCO_F64 = 0, 1, 2, 3
@@ -48,6 +50,12 @@ SIGNATURES = {
     "loco_encode": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "loco_host_workspace_bytes": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "loco_encode_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "loco_plan_create": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int, C.POINTER(_H)]),
+    "loco_plan_info": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_size_t)]),
+    "loco_encode_planned": (C.c_int, [_H, _H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "loco_plan_destroy": (None, [_H, _H]),
+    "loco_sync_check": (C.c_int, [_H, C.c_void_p]),
+    "loco_is_debug_build": (C.c_int, []),
     "loco_plan_text": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_size_t)]),
     "loco_encode_text": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "loco_set_head": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -63,11 +71,12 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
-_lib = None
+_libs = {}
 
 
 def build(verbose: bool = False) -> str:
-    """Compile the CUDA sources for sm_100a with nvcc (in-tree, so the .so travels to the GPU box)."""
+    """Compile the CUDA sources for sm_100a with nvcc (in-tree, so the .so files travel to the GPU box): the product library and
+    its LOCO_DEBUG twin."""
     r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
     if r.returncode != 0:
         raise LocoError("building libloco_asr.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
@@ -76,22 +85,25 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
-def load():
-    """dlopen the library and attach signatures.  Raises LocoError if it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise LocoError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+def load(debug: bool = False):
+    """dlopen the library and attach signatures.  Raises LocoError if it has not been built.  ``debug=True`` loads the
+    LOCO_DEBUG build (cross-check kernels + the knobs that select them), which only the tests and tools/ use."""
+    path = DEBUG_LIB_PATH if debug else LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise LocoError(f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(or `make -C loco_asr_b200/csrc`).  There is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here == header/library drift
         fn.restype = res
         fn.argtypes = args
-    if lib.loco_abi_version() != 1:
-        raise LocoError(f"ABI version mismatch: library {lib.loco_abi_version()} != binding 1")
-    _lib = lib
+    if lib.loco_abi_version() != ABI_VERSION:
+        raise LocoError(f"ABI version mismatch: library {lib.loco_abi_version()} != binding {ABI_VERSION}")
+    if bool(lib.loco_is_debug_build()) != bool(debug) and not os.environ.get("LOCO_ASR_LIB"):
+        raise LocoError(f"{path} is {'a' if lib.loco_is_debug_build() else 'not a'} LOCO_DEBUG build")
+    _libs[path] = lib
     return lib
 
 

@@ -4,8 +4,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
+#include <list>
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/loco_asr.h"
@@ -48,17 +51,32 @@ struct Layout {
     int max_t0 = 0, max_t6 = 0, max_slot6 = 0, chunks = 1;
     std::vector<UttMeta> meta;
     std::vector<PcTile> pc_tiles;
-    size_t off_pctiles = 0;
     size_t off_stats1 = 0, off_stats2 = 0;      // deferred LayerNorm: row statistics of attn_res / ffn_res, [R6, 6, 2] fp32
-    size_t off_at_tiles = 0, off_at_utts = 0;   // attention work lists: tcgen05 tiles / mma.sync utterance indices
-    size_t off_meta = 0, off_partial = 0, off_scale = 0, off_shift = 0, off_rowframe = 0;
+    size_t off_partial = 0, off_scale = 0, off_shift = 0, off_rowframe = 0;
     std::map<std::string, Buf> bufs;
-    size_t bytes = 0;
+    size_t bytes = 0;                           // caller-owned workspace: stage buffers and per-call scratch only
 };
 
 std::string g_create_error;
 
 }  // namespace
+
+// A batch geometry made ready to launch (loco_plan_create): the layout, the attention work lists, and one small device block
+// (owned by the plan) holding everything the kernels read about the batch -- utterance metadata and tile lists.  Encoding with
+// a plan enqueues kernels and memset nodes only: no host-to-device copy, no host synchronisation, hence capturable.
+struct loco_batch_plan {
+    int kind = 0;                               // 0 speech (lengths = samples), 1 text (lengths = tokens)
+    std::vector<int32_t> lengths;
+    Layout L;
+    std::vector<PcTile> at_tiles;               // tcgen05 attention work list (128-query tiles)
+    std::vector<int32_t> at_utts;               // LOCO_DEBUG builds: utterances routed to the mma.sync cross-check kernel
+    int at_ms_max_t6 = 0;
+    uint8_t* dev = nullptr;                     // [meta | pc_tiles | at_tiles | at_utts]
+    size_t d_meta = 0, d_pctiles = 0, d_attiles = 0, d_atutts = 0, dev_bytes = 0;
+    int device = 0;
+    bool cached = false;                        // owned by the handle's plan cache (loco_encode), not by the caller
+    uint64_t knobs = 0;                         // debug-knob state the work lists were built under
+};
 
 struct loco_handle {
     loco_config cfg;
@@ -95,12 +113,16 @@ struct loco_handle {
     int gemm_impl = 2;          // 2 = tcgen05 CTA pair [default], 0 = tcgen05 single CTA, 1 = SIMT reference
     int posconv_impl = 0;
     int ln_impl = 0;            // 0 = LayerNorms of the transformer layers deferred into the GEMM epilogues [default], 1 = LayerNorm kernels
-    int attn_impl = -1;         // -1 = by length (tcgen05 from attn_tc_min_frames), 0 = tcgen05, 1 = mma.sync
+    int attn_impl = 0;          // 0 = tcgen05 [default, the only product kernel], 1 = mma.sync cross-check, -1 = by length (round-1 routing)
     int attn_tc_min_frames = 193;   // utterances with at least this many frames use the tcgen05 attention kernel,
     int attn_tc_lo = 76, attn_tc_hi = 128;   // ... and so do utterances that fill most of one 128-query tile (see loco_encode)
     alignas(64) CUtensorMap pe_map;   // pe_k [320, 64] for the tcgen05 attention kernel
     int stop_after_layer = -1;
-    Layout last;
+    // plans built on behalf of loco_encode / loco_encode_text, keyed by the batch's lengths (LRU): a set that is encoded
+    // batch by batch, epoch after epoch, plans each batch once
+    std::list<loco_batch_plan*> plan_lru;
+    std::unordered_map<uint64_t, std::list<loco_batch_plan*>::iterator> plan_index;
+    const loco_batch_plan* last_plan = nullptr;       // loco_debug_buffer
     void* last_ws = nullptr;
     int64_t launches = 0;
     // optional per-stage CUDA-event timing (bench.py roofline): one event pair per launch
@@ -131,7 +153,7 @@ int fail(loco_handle* h, int code, const std::string& msg) {
 size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
 
 // The stage buffers inside the workspace want 1024-byte alignment (TMA boxes, SWIZZLE_128B atoms).  The caller's pointer
-// may have any alignment (cudaMalloc promises 256 B, torch's caching allocator 512 B): loco_plan* report kWsSlack bytes more
+// may have any alignment (cudaMalloc promises 256 B, torch's caching allocator 512 B): loco_batch_plan* report kWsSlack bytes more
 // than the layout needs and the encode calls round the base up themselves.
 constexpr size_t kWsSlack = 1024;
 constexpr int kMaxUtts = 65535;     // utterances per call: the per-utterance kernels index them with gridDim.y / gridDim.x
@@ -304,9 +326,6 @@ int make_layout_text(loco_handle* h, const int32_t* n_tokens, int n_utts, Layout
         p = align_up(p + bytes);
         return o;
     };
-    L->off_meta = take((size_t)n_utts * sizeof(UttMeta));
-    L->off_at_tiles = take(L->pc_tiles.size() * sizeof(PcTile));
-    L->off_at_utts = take((size_t)n_utts * sizeof(int32_t));
     L->off_stats1 = take((size_t)L->R6 * 2 * kStatSlots * sizeof(float));
     L->off_stats2 = take((size_t)L->R6 * 2 * kStatSlots * sizeof(float));
     L->off_rowframe = take((size_t)L->R6 * sizeof(int32_t));
@@ -376,10 +395,6 @@ int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L)
         p = align_up(p + bytes);
         return o;
     };
-    L->off_meta = take((size_t)n_utts * sizeof(UttMeta));
-    L->off_pctiles = take(L->pc_tiles.size() * sizeof(PcTile));
-    L->off_at_tiles = take(L->pc_tiles.size() * sizeof(PcTile));
-    L->off_at_utts = take((size_t)n_utts * sizeof(int32_t));
     L->off_partial = take((size_t)n_utts * L->chunks * 65 * sizeof(double));
     L->off_scale = take((size_t)n_utts * kConvDim * sizeof(float));
     L->off_shift = take((size_t)n_utts * kConvDim * sizeof(float));
@@ -449,7 +464,11 @@ void prof_break(loco_handle* h) { h->prof_last_end = nullptr; }
 
 int run_gemm(loco_handle* h, const GemmArgs& g, cudaStream_t s) {
     prof_begin(h, CAT_GEMM, s);
+#ifdef LOCO_DEBUG
     int rc = h->gemm_impl == 1 ? gemm_simt_launch(g, s) : h->gemm_impl == 2 ? gemm_tc2_launch(g, h->num_sms, s) : gemm_tc_launch(g, h->num_sms, s);
+#else
+    int rc = gemm_tc2_launch(g, h->num_sms, s);
+#endif
     prof_end(h, s);
     h->launches += 1;
     if (rc) return fail(h, LOCO_ERR_CUDA, std::string("gemm launch failed: ") + cudaGetErrorString((cudaError_t)rc));
@@ -464,6 +483,22 @@ int run_gemm(loco_handle* h, const GemmArgs& g, cudaStream_t s) {
         h->launches += (n);                                                                                    \
         if (rc_) return fail(h, LOCO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)rc_)); \
     } while (0)
+
+// No C++ exception may cross the C boundary (std::bad_alloc / std::length_error from the host-side vectors).
+template <typename F>
+int guarded(loco_handle* h, const char* what, F&& f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        return fail(h, LOCO_ERR_INVALID, std::string(what) + ": out of host memory");
+    } catch (const std::exception& e) {
+        return fail(h, LOCO_ERR_INVALID, std::string(what) + ": " + e.what());
+    } catch (...) {
+        return fail(h, LOCO_ERR_INVALID, std::string(what) + ": unknown C++ exception");
+    }
+}
+
+void clear_plan_cache(loco_handle* h);
 
 }  // namespace
 
@@ -550,13 +585,16 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
     h->cfg = *cfg;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
-    int rc = gemm_tc_init();
+    int rc = tensormap_init();
     if (!rc) rc = gemm_tc2_init();
-    if (!rc) rc = attention_init();
     if (!rc) rc = attention_tc_init();
-    if (!rc) rc = posconv_init();
     if (!rc) rc = posconv_tc_init();
     if (!rc) rc = frontend_init();
+#ifdef LOCO_DEBUG
+    if (!rc) rc = gemm_tc_init();
+    if (!rc) rc = attention_init();
+    if (!rc) rc = posconv_init();
+#endif
     if (rc) {
         g_create_error = std::string("kernel init failed: ") + cudaGetErrorString((cudaError_t)rc);
         delete h;
@@ -569,13 +607,18 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
 void loco_destroy(loco_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    clear_plan_cache(h);
     for (void* p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
 
+static int load_tensor_impl(loco_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype);
 int loco_load_tensor(loco_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype) {
     if (!h || !key || !data || ndim < 0 || ndim > 4) return fail(h, LOCO_ERR_INVALID, "loco_load_tensor: bad argument");
+    return guarded(h, "loco_load_tensor", [&]() -> int { return load_tensor_impl(h, key, data, shape, ndim, dtype); });
+}
+static int load_tensor_impl(loco_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype) {
     if (h->finalized) return fail(h, LOCO_ERR_STATE, "weights already finalized");
     const std::string k = canon_key(key);
     if (k == "prenet.masked_spec_embed" || k.find("pos_sinusoidal_embed") != std::string::npos || k == "prenet.encode_positions.pe")
@@ -603,8 +646,12 @@ int loco_load_tensor(loco_handle* h, const char* key, const void* data, const in
     return LOCO_OK;
 }
 
+static int finalize_impl(loco_handle* h);
 int loco_finalize_weights(loco_handle* h) {
     if (!h) return LOCO_ERR_INVALID;
+    return guarded(h, "loco_finalize_weights", [&]() -> int { return finalize_impl(h); });
+}
+static int finalize_impl(loco_handle* h) {
     if (h->finalized) return fail(h, LOCO_ERR_STATE, "weights already finalized");
     CK(cudaSetDevice(h->device));
     int rc;
@@ -664,7 +711,9 @@ int loco_finalize_weights(loco_handle* h) {
                     w[(gj * 48 + (o % 48)) * 48 + c] = to_bf16_host(val);
                     wt[((gj * 6 + c / 8) * 48 + (o % 48)) * 8 + (c % 8)] = to_bf16_host(val);
                 }
+#ifdef LOCO_DEBUG
         if ((rc = upload(h, w, &h->pos_w))) return rc;
+#endif
         if ((rc = upload(h, wt, &h->pos_w_tc))) return rc;
         if ((rc = upload_f32(h, "prenet.pos_conv_embed.conv.bias", {768}, &h->pos_b))) return rc;
     }
@@ -776,41 +825,169 @@ int loco_finalize_weights(loco_handle* h) {
     return LOCO_OK;
 }
 
-// The 12 post-LN transformer layers + final LayerNorm / masked mean-pool, shared by the speech and the text paths
-// (SpeechT5Encoder.forward, HF modeling_speecht5.py:1250-1338).  Expects B("x") = encoder input after its LayerNorm and
-// the per-utterance metadata already in the workspace.
-static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, float* pooled_dev, float* hidden_dev, cudaStream_t s) {
-    int rc;
-    auto B = [&](const char* name) { return reinterpret_cast<bf16*>(ws + L.bufs[name].off); };
-    UttMeta* meta = reinterpret_cast<UttMeta*>(ws + L.off_meta);
-    const int R6 = (int)L.R6;
-    // ---- attention work lists.  The kernel is chosen PER UTTERANCE by its own frame count, never by its batch-mates, so
-    // an utterance's result does not depend on the batch it travels in.  Measured with tools/attn_sweep.py (ms per layer
-    // at 64k frames, tcgen05 / mma.sync): 64 frames 0.36 / 0.22, 72: 0.34 / 0.34, 80: 0.31 / 0.32, 96: 0.28 / 0.31, 128: 0.24 / 0.31,
-    // 132: 0.58 / 0.44, 160: 0.50 / 0.40, 192: 0.45 / 0.40, 208: 0.42 / 0.51, 499: 0.47 / 0.87, 2999: 1.60 / 3.3.  The persistent tcgen05 kernel pays a fixed
-    // cost per 128-query tile, so it loses where the second tile is mostly empty (129..192 frames) and on very short
-    // utterances; the mma.sync kernel works in 64-query tiles, 3-4 CTAs/SM.
-    std::vector<PcTile> at_tiles;
-    std::vector<int32_t> at_utts;
-    int at_ms_max_t6 = 0;
+}  // extern "C"
+
+// ---- plans -----------------------------------------------------------------------------------------------------------
+namespace {
+
+uint64_t knob_state(const loco_handle* h) {
+    return ((uint64_t)(uint32_t)(h->attn_impl + 1) << 48) ^ ((uint64_t)(uint32_t)h->attn_tc_min_frames << 32) ^
+           ((uint64_t)(uint32_t)h->attn_tc_lo << 16) ^ (uint64_t)(uint32_t)h->attn_tc_hi;
+}
+
+uint64_t hash_lengths(int kind, const int32_t* v, int n) {
+    uint64_t x = 1469598103934665603ull ^ (uint64_t)kind;
+    for (int i = 0; i < n; ++i) {
+        x ^= (uint64_t)(uint32_t)v[i];
+        x *= 1099511628211ull;
+    }
+    return x ^ ((uint64_t)n << 40);
+}
+
+void free_plan(loco_batch_plan* p) {
+    if (!p) return;
+    if (p->dev) {
+        cudaSetDevice(p->device);
+        cudaFree(p->dev);
+    }
+    delete p;
+}
+
+// Geometry + work lists + the device block.  Synchronous (cudaMalloc / cudaMemcpy): plan outside captures and hot loops.
+int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loco_batch_plan** out) {
+    if (!h->finalized) return fail(h, LOCO_ERR_STATE, "plan before loco_finalize_weights");
+    if (kind == 0 && !h->has_speech) return fail(h, LOCO_ERR_STATE, "this handle was loaded without the speech prenet (text-only weights)");
+    if (kind == 1 && !h->has_text) return fail(h, LOCO_ERR_STATE, "this handle was loaded without the text prenet (prenet.embed_tokens.weight)");
+    loco_batch_plan* p = new loco_batch_plan();
+    p->kind = kind;
+    p->device = h->device;
+    p->lengths.assign(lengths, lengths + n_utts);
+    p->knobs = knob_state(h);
+    int rc = kind == 0 ? make_layout(h, lengths, n_utts, &p->L) : make_layout_text(h, lengths, n_utts, &p->L);
+    if (rc) {
+        delete p;
+        return rc;
+    }
+    Layout& L = p->L;
+    // ---- attention work list: every utterance's 128-query tiles go to the tcgen05 kernel.  (LOCO_DEBUG builds can route
+    // utterances to the mma.sync cross-check kernel, chosen PER UTTERANCE by its own frame count, never by its batch-mates.)
     for (int u = 0; u < n_utts; ++u) {
         const int t6 = L.meta[u].t6;
-        const bool tc = h->attn_impl == 0 ||
-                        (h->attn_impl < 0 && (t6 >= h->attn_tc_min_frames || (t6 >= h->attn_tc_lo && t6 <= h->attn_tc_hi)));
+        bool tc = true;
+#ifdef LOCO_DEBUG
+        tc = h->attn_impl == 0 || (h->attn_impl < 0 && (t6 >= h->attn_tc_min_frames || (t6 >= h->attn_tc_lo && t6 <= h->attn_tc_hi)));
+#endif
         if (tc) {
-            for (int f = 0; f < t6; f += 128) at_tiles.push_back({L.meta[u].row6 + f, f, t6, 0});
+            for (int f = 0; f < t6; f += 128) p->at_tiles.push_back({L.meta[u].row6 + f, f, t6, 0});
         } else {
-            at_utts.push_back(u);
-            if (t6 > at_ms_max_t6) at_ms_max_t6 = t6;
+            p->at_utts.push_back(u);
+            if (t6 > p->at_ms_max_t6) p->at_ms_max_t6 = t6;
         }
     }
-    PcTile* at_tiles_dev = reinterpret_cast<PcTile*>(ws + L.off_at_tiles);
-    int32_t* at_utts_dev = reinterpret_cast<int32_t*>(ws + L.off_at_utts);
-    if (!at_tiles.empty()) CK(cudaMemcpyAsync(at_tiles_dev, at_tiles.data(), at_tiles.size() * sizeof(PcTile), cudaMemcpyHostToDevice, s));
-    if (!at_utts.empty()) CK(cudaMemcpyAsync(at_utts_dev, at_utts.data(), at_utts.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess) {
+        // position tables grow on demand, as HF's do (HF:331-333); done here so that encoding never synchronises
+        if (kind == 0 && L.max_t6 + h->cfg.pad_token_id + 1 >= h->sin_rows) {
+            e = cudaDeviceSynchronize();
+            if (e == cudaSuccess && (rc = build_sin_table(h, L.max_t6 + h->cfg.pad_token_id + 1024))) {
+                delete p;
+                return rc;
+            }
+        }
+        if (kind == 1 && L.max_t6 > h->txt_pe_rows) {      // HF's table stops at max_text_positions (450); this one grows
+            e = cudaDeviceSynchronize();
+            if (e == cudaSuccess && (rc = build_text_pe(h, L.max_t6 + 1024))) {
+                delete p;
+                return rc;
+            }
+        }
+    }
+    auto place = [&](size_t bytes) {
+        size_t o = p->dev_bytes;
+        p->dev_bytes = (p->dev_bytes + bytes + 255) / 256 * 256;
+        return o;
+    };
+    p->d_meta = place((size_t)n_utts * sizeof(UttMeta));
+    p->d_pctiles = place(L.pc_tiles.size() * sizeof(PcTile));
+    p->d_attiles = place(p->at_tiles.size() * sizeof(PcTile));
+    p->d_atutts = place(p->at_utts.size() * sizeof(int32_t));
+    if (p->dev_bytes == 0) p->dev_bytes = 256;
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->dev), p->dev_bytes);
+    auto up = [&](size_t off, const void* src, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(p->dev + off, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up(p->d_meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta));
+    up(p->d_pctiles, L.pc_tiles.data(), L.pc_tiles.size() * sizeof(PcTile));
+    up(p->d_attiles, p->at_tiles.data(), p->at_tiles.size() * sizeof(PcTile));
+    up(p->d_atutts, p->at_utts.data(), p->at_utts.size() * sizeof(int32_t));
+    if (e != cudaSuccess) {
+        free_plan(p);
+        return fail(h, LOCO_ERR_CUDA, std::string("loco_plan_create: ") + cudaGetErrorString(e));
+    }
+    *out = p;
+    return LOCO_OK;
+}
+
+constexpr size_t kPlanCacheSize = 256;
+
+void clear_plan_cache(loco_handle* h) {
+    for (loco_batch_plan* p : h->plan_lru) free_plan(p);
+    h->plan_lru.clear();
+    h->plan_index.clear();
+    h->last_plan = nullptr;
+}
+
+// The plan of this batch, built on first sight (that call synchronises the device once) and reused afterwards.
+int cached_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, const loco_batch_plan** out) {
+    const uint64_t key = hash_lengths(kind, lengths, n_utts);
+    auto it = h->plan_index.find(key);
+    if (it != h->plan_index.end()) {
+        loco_batch_plan* p = *it->second;
+        if (p->kind == kind && (int)p->lengths.size() == n_utts && p->knobs == knob_state(h) &&
+            std::equal(lengths, lengths + n_utts, p->lengths.begin())) {
+            h->plan_lru.splice(h->plan_lru.begin(), h->plan_lru, it->second);
+            *out = p;
+            return LOCO_OK;
+        }
+        if (h->last_plan == p) h->last_plan = nullptr;
+        free_plan(p);                       // same hash, different batch (or stale knobs): replace
+        h->plan_lru.erase(it->second);
+        h->plan_index.erase(it);
+    }
+    loco_batch_plan* p = nullptr;
+    int rc = build_plan(h, kind, lengths, n_utts, &p);
+    if (rc) return rc;
+    p->cached = true;
+    h->plan_lru.push_front(p);
+    h->plan_index[key] = h->plan_lru.begin();
+    if (h->plan_lru.size() > kPlanCacheSize) {
+        loco_batch_plan* old = h->plan_lru.back();
+        h->plan_index.erase(hash_lengths(old->kind, old->lengths.data(), (int)old->lengths.size()));
+        h->plan_lru.pop_back();
+        if (h->last_plan == old) h->last_plan = nullptr;
+        free_plan(old);                     // cudaFree waits for work that may still read the block
+    }
+    *out = p;
+    return LOCO_OK;
+}
+
+}  // namespace
+
+// The 12 post-LN transformer layers + final LayerNorm / masked mean-pool, shared by the speech and the text paths
+// (SpeechT5Encoder.forward, HF modeling_speecht5.py:1250-1338).  Expects B("x") = encoder input after its LayerNorm.
+static int run_transformer(loco_handle* h, const loco_batch_plan& P, uint8_t* ws, float* pooled_dev, float* hidden_dev, cudaStream_t s) {
+    int rc;
+    const Layout& L = P.L;
+    const int n_utts = L.n_utts;
+    auto B = [&](const char* name) { return reinterpret_cast<bf16*>(ws + L.bufs.at(name).off); };
+    const UttMeta* meta = reinterpret_cast<const UttMeta*>(P.dev + P.d_meta);
+    const int R6 = (int)L.R6;
+    const PcTile* at_tiles_dev = reinterpret_cast<const PcTile*>(P.dev + P.d_attiles);
+    const int32_t* at_utts_dev = reinterpret_cast<const int32_t*>(P.dev + P.d_atutts);
+    (void)at_utts_dev;
     // slot padding rows of ctx are never written by the attention kernels; keep them finite (zero) so they stay finite
     // through every later layer -- the tcgen05 attention multiplies masked (P = 0) key rows into O, and 0 * NaN = NaN
-    CK(cudaMemsetAsync(ws + L.bufs["ctx"].off, 0, (size_t)L.R6 * kHidden * sizeof(bf16), s));
+    CK(cudaMemsetAsync(ws + L.bufs.at("ctx").off, 0, (size_t)L.R6 * kHidden * sizeof(bf16), s));
     prof_break(h);
     alignas(64) CUtensorMap qkv_map;
     if (make_tensor_map_bf16_sw128(&qkv_map, B("qkv"), 3 * kHidden, (uint64_t)L.R6, 3 * kHidden, 32))
@@ -838,10 +1015,12 @@ static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, f
             g.W = w.wqkv; g.bias = w.bqkv; g.epilogue = EPI_BIAS;
         }
         if ((rc = run_gemm(h, g, s))) return rc;
-        if (!at_utts.empty())
-            LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, at_utts_dev, (int)at_utts.size(), at_ms_max_t6, B("ctx"), s), 1);
-        if (!at_tiles.empty())
-            LAUNCH(CAT_ATTENTION, launch_attention_tc(&qkv_map, &h->pe_map, at_tiles_dev, (int)at_tiles.size(), B("ctx"), h->num_sms, s), 1);
+#ifdef LOCO_DEBUG
+        if (!P.at_utts.empty())
+            LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, at_utts_dev, (int)P.at_utts.size(), P.at_ms_max_t6, B("ctx"), s), 1);
+#endif
+        if (!P.at_tiles.empty())
+            LAUNCH(CAT_ATTENTION, launch_attention_tc(&qkv_map, &h->pe_map, at_tiles_dev, (int)P.at_tiles.size(), B("ctx"), h->num_sms, s), 1);
         g = GemmArgs();
         g.A = B("ctx"); g.lda = kHidden; g.a_rows_alloc = R6; g.W = w.wo; g.C = B("attn_res"); g.ldc = kHidden;
         g.bias = w.bo; g.ldr = kHidden; g.M = R6; g.N = kHidden; g.K = kHidden;
@@ -883,64 +1062,48 @@ static int run_transformer(loco_handle* h, Layout& L, uint8_t* ws, int n_utts, f
     return LOCO_OK;
 }
 
-int loco_plan(loco_handle* h, const int32_t* n_samples, int n_utts, int32_t* frames, int32_t* rows, int64_t* total_frames,
-              size_t* workspace_bytes) {
-    if (!h || (!n_samples && n_utts > 0)) return fail(h, LOCO_ERR_INVALID, "loco_plan: bad argument");
-    Layout L;
-    int rc = make_layout(h, n_samples, n_utts, &L);
-    if (rc) return rc;
-    for (int u = 0; u < n_utts; ++u) {
-        if (frames) frames[u] = L.meta[u].t6;
-        if (rows) rows[u] = L.meta[u].row6;
-    }
-    if (total_frames) *total_frames = L.total_frames;
-    if (workspace_bytes) *workspace_bytes = L.bytes + kWsSlack;
-    return LOCO_OK;
-}
+namespace {
 
-int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples, int n_utts, float* pooled_dev, float* hidden_dev,
-                void* workspace_dev, size_t workspace_bytes, void* stream) {
-    if (!h) return LOCO_ERR_INVALID;
-    if (!h->finalized) return fail(h, LOCO_ERR_STATE, "loco_encode before loco_finalize_weights");
-    if (!h->has_speech) return fail(h, LOCO_ERR_STATE, "loco_encode: this handle was loaded without the speech prenet (text-only weights)");
+// Everything loco_encode / loco_encode_text / loco_encode_planned enqueue.  Kernels and memset nodes only.
+int encode_with_plan(loco_handle* h, const loco_batch_plan& P, const void* input_dev, float* pooled_dev, float* hidden_dev, void* workspace_dev,
+                     size_t workspace_bytes, cudaStream_t s) {
+    const Layout& L = P.L;
+    const int n_utts = L.n_utts;
     if (n_utts == 0) return LOCO_OK;
-    if (!wave_dev || !n_samples || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode: null argument");
-    if ((reinterpret_cast<uintptr_t>(wave_dev) & 3) != 0) return fail(h, LOCO_ERR_INVALID, "wave_dev must be 4-byte aligned");
-    prof_break(h);
-    Layout& L = h->last;
-    L = Layout();
-    int rc = make_layout(h, n_samples, n_utts, &L);
-    if (rc) return rc;
+    if (!input_dev || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "encode: null argument");
+    if ((reinterpret_cast<uintptr_t>(input_dev) & 3) != 0) return fail(h, LOCO_ERR_INVALID, "the input buffer must be 4-byte aligned");
+    if (P.device != h->device) return fail(h, LOCO_ERR_INVALID, "plan belongs to another device");
     uint8_t* ws = nullptr;
     if (!carve_workspace(workspace_dev, workspace_bytes, L.bytes, &ws))
         return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes + kWsSlack) +
-                                               " bytes (loco_plan's workspace_bytes), got " + std::to_string(workspace_bytes));
+                                               " bytes (the plan's workspace_bytes), got " + std::to_string(workspace_bytes));
     CK(cudaSetDevice(h->device));
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (L.max_t6 + h->cfg.pad_token_id + 1 >= h->sin_rows) {  // HF grows its table on demand too (HF:331-333)
-        CK(cudaStreamSynchronize(s));
-        if ((rc = build_sin_table(h, L.max_t6 + h->cfg.pad_token_id + 1024))) return rc;
-    }
+    prof_break(h);
+    h->last_plan = &P;
     h->last_ws = ws;
-    auto B = [&](const char* name) { return reinterpret_cast<bf16*>(ws + L.bufs[name].off); };
-    UttMeta* meta = reinterpret_cast<UttMeta*>(ws + L.off_meta);
+    int rc;
+    auto B = [&](const char* name) { return reinterpret_cast<bf16*>(ws + L.bufs.at(name).off); };
+    const UttMeta* meta = reinterpret_cast<const UttMeta*>(P.dev + P.d_meta);
+    int32_t* row_frame = reinterpret_cast<int32_t*>(ws + L.off_rowframe);
+    const int R6 = (int)L.R6;
+    LAUNCH(CAT_ROWOPS, launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
+    if (P.kind == 1) {
+        LAUNCH(CAT_ROWOPS, launch_text_prenet_ln(reinterpret_cast<const int32_t*>(input_dev), h->txt_embed, h->txt_pe, h->txt_alpha, h->txt_vocab,
+                                                 row_frame, B("x"), h->eln_w, h->eln_b, R6, s), 1);
+        return run_transformer(h, P, ws, pooled_dev, hidden_dev, s);
+    }
+    const float* wave_dev = reinterpret_cast<const float*>(input_dev);
     double* partial = reinterpret_cast<double*>(ws + L.off_partial);
     float* scale = reinterpret_cast<float*>(ws + L.off_scale);
     float* shift = reinterpret_cast<float*>(ws + L.off_shift);
-    int32_t* row_frame = reinterpret_cast<int32_t*>(ws + L.off_rowframe);
-    const int R6 = (int)L.R6;
-
-    // pageable source: the runtime stages the bytes before returning, so `L.meta` may be reused at once
-    CK(cudaMemcpyAsync(meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta), cudaMemcpyHostToDevice, s));
-    PcTile* pc_tiles = reinterpret_cast<PcTile*>(ws + L.off_pctiles);
-    CK(cudaMemcpyAsync(pc_tiles, L.pc_tiles.data(), L.pc_tiles.size() * sizeof(PcTile), cudaMemcpyHostToDevice, s));
+    const PcTile* pc_tiles = reinterpret_cast<const PcTile*>(P.dev + P.d_pctiles);
     for (int i = 0; i < 6; ++i) {  // the 8 pad frames the last implicit-GEMM rows of layer i+1 may touch
         char nm[16];
         snprintf(nm, sizeof nm, "conv%d", i);
-        const Buf& b = L.bufs[nm];
+        const Buf& b = L.bufs.at(nm);
         CK(cudaMemsetAsync(ws + b.off + (size_t)b.rows * kConvDim * 2, 0, (size_t)8 * kConvDim * 2, s));
     }
-    LAUNCH(CAT_ROWOPS, launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
+    prof_break(h);
     // ---- conv feature encoder -----------------------------------------------------------------------
     LAUNCH(CAT_FRONTEND, launch_wave_stats(wave_dev, meta, n_utts, L.chunks, h->w0, h->gn_w, h->gn_b, partial, scale, shift, s), 2);
     LAUNCH(CAT_FRONTEND, launch_conv0(wave_dev, meta, n_utts, L.max_slot6 << 6, h->w0, scale, shift, B("conv0"), s), 1);
@@ -949,7 +1112,7 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         snprintf(in, sizeof in, "conv%d", i - 1);
         snprintf(out, sizeof out, "conv%d", i);
         const int K = h->cfg.conv_kernel[i] * kConvDim;
-        const int64_t rows_in = L.bufs[in].rows + 8;
+        const int64_t rows_in = L.bufs.at(in).rows + 8;
         GemmArgs g = {};
         g.A = B(in);
         g.lda = 2 * kConvDim;
@@ -957,7 +1120,7 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         g.W = h->conv_w[i];
         g.C = B(out);
         g.ldc = kConvDim;
-        g.M = (int)L.bufs[out].rows;
+        g.M = (int)L.bufs.at(out).rows;
         g.N = kConvDim;
         g.K = K;
         g.epilogue = EPI_BIAS_GELU;
@@ -971,23 +1134,101 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
         g.bias = h->proj_b; g.M = R6; g.N = kHidden; g.K = kConvDim; g.epilogue = EPI_BIAS;
         if ((rc = run_gemm(h, g, s))) return rc;
     }
+#ifdef LOCO_DEBUG
     if (h->posconv_impl == 1)
         LAUNCH(CAT_POSCONV, launch_posconv(B("proj"), h->pos_w, h->pos_b, meta, n_utts, L.max_t6, B("pos_conv"), s), 1);
     else
+#endif
         LAUNCH(CAT_POSCONV, launch_posconv_tc(B("proj"), h->pos_w_tc, h->pos_b, pc_tiles, (int)L.pc_tiles.size(), B("pos_conv"), s), 1);
     LAUNCH(CAT_ROWOPS, launch_prenet_ln(B("proj"), B("pos_conv"), h->sin_table, row_frame, B("x"), h->eln_w, h->eln_b, R6, s), 1);
+    return run_transformer(h, P, ws, pooled_dev, hidden_dev, s);
+}
 
-    return run_transformer(h, L, ws, n_utts, pooled_dev, hidden_dev, s);
+}  // namespace
+
+extern "C" {
+
+int loco_plan(loco_handle* h, const int32_t* n_samples, int n_utts, int32_t* frames, int32_t* rows, int64_t* total_frames,
+              size_t* workspace_bytes) {
+    if (!h || (!n_samples && n_utts > 0)) return fail(h, LOCO_ERR_INVALID, "loco_plan: bad argument");
+    return guarded(h, "loco_plan", [&]() -> int {
+        Layout L;
+        int rc = make_layout(h, n_samples, n_utts, &L);
+        if (rc) return rc;
+        for (int u = 0; u < n_utts; ++u) {
+            if (frames) frames[u] = L.meta[u].t6;
+            if (rows) rows[u] = L.meta[u].row6;
+        }
+        if (total_frames) *total_frames = L.total_frames;
+        if (workspace_bytes) *workspace_bytes = L.bytes + kWsSlack;
+        return LOCO_OK;
+    });
+}
+
+int loco_plan_create(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loco_batch_plan** out) {
+    if (!h || !out || (!lengths && n_utts > 0) || kind < 0 || kind > 1) return fail(h, LOCO_ERR_INVALID, "loco_plan_create: bad argument");
+    return guarded(h, "loco_plan_create", [&]() -> int { return build_plan(h, kind, lengths, n_utts, out); });
+}
+
+int loco_plan_info(const loco_batch_plan* p, int32_t* frames, int32_t* rows, int64_t* total_frames, size_t* workspace_bytes) {
+    if (!p) return LOCO_ERR_INVALID;
+    for (int u = 0; u < p->L.n_utts; ++u) {
+        if (frames) frames[u] = p->L.meta[u].t6;
+        if (rows) rows[u] = p->L.meta[u].row6;
+    }
+    if (total_frames) *total_frames = p->L.total_frames;
+    if (workspace_bytes) *workspace_bytes = p->L.bytes + kWsSlack;
+    return LOCO_OK;
+}
+
+void loco_plan_destroy(loco_handle* h, loco_batch_plan* p) {
+    if (!p || p->cached) return;
+    if (h && h->last_plan == p) h->last_plan = nullptr;
+    free_plan(p);
+}
+
+int loco_encode_planned(loco_handle* h, const loco_batch_plan* plan, const void* input_dev, float* pooled_dev, float* hidden_dev,
+                        void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h) return LOCO_ERR_INVALID;
+    if (!plan) return fail(h, LOCO_ERR_INVALID, "loco_encode_planned: null plan");
+    return guarded(h, "loco_encode_planned", [&]() -> int {
+        return encode_with_plan(h, *plan, input_dev, pooled_dev, hidden_dev, workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+    });
+}
+
+int loco_sync_check(loco_handle* h, void* stream) {
+    if (!h) return LOCO_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+    CK(cudaGetLastError());
+    return LOCO_OK;
+}
+
+int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples, int n_utts, float* pooled_dev, float* hidden_dev,
+                void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h) return LOCO_ERR_INVALID;
+    if (!h->finalized) return fail(h, LOCO_ERR_STATE, "loco_encode before loco_finalize_weights");
+    if (!h->has_speech) return fail(h, LOCO_ERR_STATE, "loco_encode: this handle was loaded without the speech prenet (text-only weights)");
+    if (n_utts == 0) return LOCO_OK;
+    if (!wave_dev || !n_samples || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode: null argument");
+    return guarded(h, "loco_encode", [&]() -> int {
+        const loco_batch_plan* plan = nullptr;
+        int rc = cached_plan(h, 0, n_samples, n_utts, &plan);
+        if (rc) return rc;
+        return encode_with_plan(h, *plan, wave_dev, pooled_dev, hidden_dev, workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+    });
 }
 
 int loco_host_workspace_bytes(loco_handle* h, const int32_t* n_samples, int n_utts, int want_hidden, size_t* bytes) {
     if (!h || !bytes || (!n_samples && n_utts > 0)) return fail(h, LOCO_ERR_INVALID, "loco_host_workspace_bytes: bad argument");
-    Layout L;
-    int rc = make_layout(h, n_samples, n_utts, &L);
-    if (rc) return rc;
-    *bytes = kWsSlack + L.bytes + align_up((size_t)L.total_samples * sizeof(float)) + align_up((size_t)n_utts * kHidden * sizeof(float)) +
-             (want_hidden ? align_up((size_t)L.total_frames * kHidden * sizeof(float)) : 0);
-    return LOCO_OK;
+    return guarded(h, "loco_host_workspace_bytes", [&]() -> int {
+        Layout L;
+        int rc = make_layout(h, n_samples, n_utts, &L);
+        if (rc) return rc;
+        *bytes = kWsSlack + L.bytes + align_up((size_t)L.total_samples * sizeof(float)) + align_up((size_t)n_utts * kHidden * sizeof(float)) +
+                 (want_hidden ? align_up((size_t)L.total_frames * kHidden * sizeof(float)) : 0);
+        return LOCO_OK;
+    });
 }
 
 int loco_encode_host(loco_handle* h, const float* wave_host, const int32_t* n_samples, int n_utts, float* pooled_host,
@@ -995,41 +1236,47 @@ int loco_encode_host(loco_handle* h, const float* wave_host, const int32_t* n_sa
     if (!h) return LOCO_ERR_INVALID;
     if (n_utts == 0) return LOCO_OK;
     if (!wave_host || !n_samples || !pooled_host || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode_host: null argument");
-    Layout L;
-    int rc = make_layout(h, n_samples, n_utts, &L);
-    if (rc) return rc;
-    const size_t wave_bytes = (size_t)L.total_samples * sizeof(float);
-    const size_t pooled_bytes = (size_t)n_utts * kHidden * sizeof(float);
-    const size_t hidden_bytes = hidden_host ? (size_t)L.total_frames * kHidden * sizeof(float) : 0;
-    const size_t need = L.bytes + align_up(wave_bytes) + align_up(pooled_bytes) + align_up(hidden_bytes);
-    uint8_t* ws = nullptr;
-    if (!carve_workspace(workspace_dev, workspace_bytes, need, &ws))
-        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small for host encode: need " + std::to_string(need + kWsSlack) +
-                                               " bytes (loco_host_workspace_bytes), got " + std::to_string(workspace_bytes));
-    CK(cudaSetDevice(h->device));
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    float* wave_dev = reinterpret_cast<float*>(ws + L.bytes);
-    float* pooled_dev = reinterpret_cast<float*>(ws + L.bytes + align_up(wave_bytes));
-    float* hidden_dev = hidden_host ? reinterpret_cast<float*>(ws + L.bytes + align_up(wave_bytes) + align_up(pooled_bytes)) : nullptr;
-    CK(cudaMemcpyAsync(wave_dev, wave_host, wave_bytes, cudaMemcpyHostToDevice, s));
-    rc = loco_encode(h, wave_dev, n_samples, n_utts, pooled_dev, hidden_dev, ws, L.bytes, stream);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(pooled_host, pooled_dev, pooled_bytes, cudaMemcpyDeviceToHost, s));
-    if (hidden_host) CK(cudaMemcpyAsync(hidden_host, hidden_dev, hidden_bytes, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    return LOCO_OK;
+    if (!h->finalized) return fail(h, LOCO_ERR_STATE, "loco_encode_host before loco_finalize_weights");
+    return guarded(h, "loco_encode_host", [&]() -> int {
+        const loco_batch_plan* plan = nullptr;
+        int rc = cached_plan(h, 0, n_samples, n_utts, &plan);
+        if (rc) return rc;
+        const Layout& L = plan->L;
+        const size_t wave_bytes = (size_t)L.total_samples * sizeof(float);
+        const size_t pooled_bytes = (size_t)n_utts * kHidden * sizeof(float);
+        const size_t hidden_bytes = hidden_host ? (size_t)L.total_frames * kHidden * sizeof(float) : 0;
+        const size_t need = L.bytes + align_up(wave_bytes) + align_up(pooled_bytes) + align_up(hidden_bytes);
+        uint8_t* ws = nullptr;
+        if (!carve_workspace(workspace_dev, workspace_bytes, need, &ws))
+            return fail(h, LOCO_ERR_WORKSPACE, "workspace too small for host encode: need " + std::to_string(need + kWsSlack) +
+                                                   " bytes (loco_host_workspace_bytes), got " + std::to_string(workspace_bytes));
+        CK(cudaSetDevice(h->device));
+        cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+        float* wave_dev = reinterpret_cast<float*>(ws + L.bytes);
+        float* pooled_dev = reinterpret_cast<float*>(ws + L.bytes + align_up(wave_bytes));
+        float* hidden_dev = hidden_host ? reinterpret_cast<float*>(ws + L.bytes + align_up(wave_bytes) + align_up(pooled_bytes)) : nullptr;
+        CK(cudaMemcpyAsync(wave_dev, wave_host, wave_bytes, cudaMemcpyHostToDevice, s));
+        rc = encode_with_plan(h, *plan, wave_dev, pooled_dev, hidden_dev, ws, L.bytes, s);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(pooled_host, pooled_dev, pooled_bytes, cudaMemcpyDeviceToHost, s));
+        if (hidden_host) CK(cudaMemcpyAsync(hidden_host, hidden_dev, hidden_bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return LOCO_OK;
+    });
 }
 
 int loco_plan_text(loco_handle* h, const int32_t* n_tokens, int n_utts, int32_t* rows, int64_t* total_tokens, size_t* workspace_bytes) {
     if (!h || (!n_tokens && n_utts > 0)) return fail(h, LOCO_ERR_INVALID, "loco_plan_text: bad argument");
-    Layout L;
-    int rc = make_layout_text(h, n_tokens, n_utts, &L);
-    if (rc) return rc;
-    for (int u = 0; u < n_utts; ++u)
-        if (rows) rows[u] = L.meta[u].row6;
-    if (total_tokens) *total_tokens = L.total_frames;
-    if (workspace_bytes) *workspace_bytes = L.bytes + kWsSlack;
-    return LOCO_OK;
+    return guarded(h, "loco_plan_text", [&]() -> int {
+        Layout L;
+        int rc = make_layout_text(h, n_tokens, n_utts, &L);
+        if (rc) return rc;
+        for (int u = 0; u < n_utts; ++u)
+            if (rows) rows[u] = L.meta[u].row6;
+        if (total_tokens) *total_tokens = L.total_frames;
+        if (workspace_bytes) *workspace_bytes = L.bytes + kWsSlack;
+        return LOCO_OK;
+    });
 }
 
 int loco_encode_text(loco_handle* h, const int32_t* tokens_dev, const int32_t* n_tokens, int n_utts, float* pooled_dev, float* hidden_dev,
@@ -1039,29 +1286,12 @@ int loco_encode_text(loco_handle* h, const int32_t* tokens_dev, const int32_t* n
     if (!h->has_text) return fail(h, LOCO_ERR_STATE, "loco_encode_text: this handle was loaded without the text prenet (prenet.embed_tokens.weight)");
     if (n_utts == 0) return LOCO_OK;
     if (!tokens_dev || !n_tokens || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode_text: null argument");
-    prof_break(h);
-    Layout& L = h->last;
-    L = Layout();
-    int rc = make_layout_text(h, n_tokens, n_utts, &L);
-    if (rc) return rc;
-    uint8_t* ws = nullptr;
-    if (!carve_workspace(workspace_dev, workspace_bytes, L.bytes, &ws))
-        return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes + kWsSlack) +
-                                               " bytes (loco_plan_text's workspace_bytes), got " + std::to_string(workspace_bytes));
-    CK(cudaSetDevice(h->device));
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (L.max_t6 > h->txt_pe_rows) {      // HF's table stops at max_text_positions (450); this one grows on demand
-        CK(cudaStreamSynchronize(s));
-        if ((rc = build_text_pe(h, L.max_t6 + 1024))) return rc;
-    }
-    h->last_ws = ws;
-    UttMeta* meta = reinterpret_cast<UttMeta*>(ws + L.off_meta);
-    int32_t* row_frame = reinterpret_cast<int32_t*>(ws + L.off_rowframe);
-    CK(cudaMemcpyAsync(meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta), cudaMemcpyHostToDevice, s));
-    LAUNCH(CAT_ROWOPS, launch_row_frames(meta, n_utts, L.max_slot6, row_frame, s), 1);
-    LAUNCH(CAT_ROWOPS, launch_text_prenet_ln(tokens_dev, h->txt_embed, h->txt_pe, h->txt_alpha, h->txt_vocab, row_frame,
-                                             reinterpret_cast<bf16*>(ws + L.bufs["x"].off), h->eln_w, h->eln_b, (int)L.R6, s), 1);
-    return run_transformer(h, L, ws, n_utts, pooled_dev, hidden_dev, s);
+    return guarded(h, "loco_encode_text", [&]() -> int {
+        const loco_batch_plan* plan = nullptr;
+        int rc = cached_plan(h, 1, n_tokens, n_utts, &plan);
+        if (rc) return rc;
+        return encode_with_plan(h, *plan, tokens_dev, pooled_dev, hidden_dev, workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+    });
 }
 
 int64_t loco_launch_count(const loco_handle* h) { return h ? h->launches : 0; }
@@ -1139,6 +1369,7 @@ int loco_set_head_outputs(loco_handle* h, float* head_pooled_dev, float* logits_
 
 int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
     if (!h || !name) return LOCO_ERR_INVALID;
+#ifdef LOCO_DEBUG
     if (!strcmp(name, "gemm_impl")) h->gemm_impl = (int)value;
     else if (!strcmp(name, "posconv_impl")) h->posconv_impl = (int)value;
     else if (!strcmp(name, "ln_impl")) h->ln_impl = (int)value;
@@ -1149,13 +1380,26 @@ int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
     else if (!strcmp(name, "stop_after_layer")) h->stop_after_layer = (int)value;
     else return fail(h, LOCO_ERR_INVALID, std::string("unknown debug knob: ") + name);
     return LOCO_OK;
+#else
+    (void)value;
+    return fail(h, LOCO_ERR_INVALID, std::string("debug knob '") + name + "': this is the product build; the cross-check kernels and "
+                                         "their switches exist only in libloco_asr_debug.so (-DLOCO_DEBUG)");
+#endif
+}
+
+int loco_is_debug_build(void) {
+#ifdef LOCO_DEBUG
+    return 1;
+#else
+    return 0;
+#endif
 }
 
 int loco_debug_buffer(loco_handle* h, const char* name, void** dev_ptr, int64_t* n_rows, int64_t* n_cols, int* dtype) {
     if (!h || !name) return LOCO_ERR_INVALID;
-    if (!h->last_ws) return fail(h, LOCO_ERR_STATE, "no encode has run yet");
-    auto it = h->last.bufs.find(name);
-    if (it == h->last.bufs.end()) return fail(h, LOCO_ERR_INVALID, std::string("unknown stage buffer: ") + name);
+    if (!h->last_ws || !h->last_plan) return fail(h, LOCO_ERR_STATE, "no encode has run yet (or its plan was destroyed)");
+    auto it = h->last_plan->L.bufs.find(name);
+    if (it == h->last_plan->L.bufs.end()) return fail(h, LOCO_ERR_INVALID, std::string("unknown stage buffer: ") + name);
     if (dev_ptr) *dev_ptr = reinterpret_cast<uint8_t*>(h->last_ws) + it->second.off;
     if (n_rows) *n_rows = it->second.rows;
     if (n_cols) *n_cols = it->second.cols;
@@ -1171,6 +1415,9 @@ int loco_debug_gemm(loco_handle* h, int impl, const void* a, int64_t lda, int64_
     g.A = reinterpret_cast<const bf16*>(a); g.lda = lda; g.a_rows_alloc = a_rows_alloc;
     g.W = reinterpret_cast<const bf16*>(w); g.C = reinterpret_cast<bf16*>(c); g.ldc = n; g.bias = bias;
     g.R = reinterpret_cast<const bf16*>(r); g.ldr = n; g.M = m; g.N = n; g.K = k; g.epilogue = epilogue;
+#ifndef LOCO_DEBUG
+    if (impl != 2) return fail(h, LOCO_ERR_INVALID, "loco_debug_gemm: only the CTA-pair kernel (impl 2) exists in the product build");
+#endif
     const int saved = h->gemm_impl;
     h->gemm_impl = impl;
     int rc = run_gemm(h, g, reinterpret_cast<cudaStream_t>(stream));

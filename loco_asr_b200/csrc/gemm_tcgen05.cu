@@ -262,21 +262,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-
 int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems, uint32_t box_rows) {
-    if (g_encode == nullptr) return (int)cudaErrorNotReady;
-    cuuint64_t dims[2] = {inner, rows};
-    cuuint64_t strides[1] = {row_stride_elems * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)r;
+    static_assert(BK == 64, "the shared tensor-map helper encodes 64-element (128-byte) boxes");
+    return make_tensor_map_bf16_sw128(map, base, inner, rows, row_stride_elems, box_rows);
 }
 
 template <int EPI>
@@ -287,28 +275,8 @@ int launch_t(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, co
 
 }  // namespace
 
-int make_tensor_map_bf16_sw128(void* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
-                               uint32_t box_rows) {
-    return make_map(reinterpret_cast<CUtensorMap*>(map), base, inner, rows, row_stride_elems, box_rows);
-}
-
-bool pdl_enabled() {
-    static const bool on = []() {
-        const char* e = getenv("LOCO_PDL");      // opt-in: measured 1.7 % SLOWER on the SLURP-shaped bench (24.15 -> 24.58 ms/step)
-        return e && e[0] == '1';
-    }();
-    return on;
-}
-
 int gemm_tc_init() {
-    if (g_encode == nullptr) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess) return (int)e;
-        if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return (int)cudaErrorNotSupported;
-        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    }
+    if (int rc = tensormap_init()) return rc;
     cudaError_t e;
     e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI_BIAS>());
     if (e != cudaSuccess) return (int)e;
@@ -322,7 +290,6 @@ int gemm_tc_launch(const GemmArgs& g, int num_sms, cudaStream_t stream) {
     if (g.M <= 0) return 0;
     if (g.N % BN != 0 || g.K % BK != 0 || (g.lda * 2) % 16 != 0 || (g.ldc % 8) != 0) return (int)cudaErrorInvalidValue;
     if (g.epilogue == EPI_BIAS_RESIDUAL && (g.R == nullptr || (g.ldr % 8) != 0)) return (int)cudaErrorInvalidValue;
-    if (g_encode == nullptr) return (int)cudaErrorNotReady;
     CUtensorMap ma, mb;
     int rc = make_map(&ma, g.A, (uint64_t)g.K, (uint64_t)g.a_rows_alloc, (uint64_t)g.lda, BM);
     if (rc) return rc;

@@ -65,12 +65,14 @@ inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
     return (int)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-// tcgen05/TMEM/TMA GEMM (gemm_tcgen05.cu).  Returns cudaError as int (0 = ok).
-int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
-int gemm_tc_launch(const GemmArgs& g, int num_sms, cudaStream_t stream);
-// 2-D bf16 tensor map, box = [64 elements (128 B), box_rows], SWIZZLE_128B (gemm_tcgen05.cu owns the driver entry point).
+// Host helpers (tensormap.cu).  Returns cudaError / CUresult as int (0 = ok).
+int tensormap_init();  // resolves cuTensorMapEncodeTiled through the runtime
+// 2-D bf16 tensor map, box = [64 elements (128 B), box_rows], SWIZZLE_128B.
 int make_tensor_map_bf16_sw128(void* map /*CUtensorMap*/, const void* base, uint64_t inner, uint64_t rows,
                                uint64_t row_stride_elems, uint32_t box_rows);
+// Single-CTA tcgen05/TMEM/TMA GEMM (gemm_tcgen05.cu): the CTA-pair kernel's predecessor, LOCO_DEBUG builds only (cross-check).
+int gemm_tc_init();
+int gemm_tc_launch(const GemmArgs& g, int num_sms, cudaStream_t stream);
 // CTA-pair variant (gemm_tcgen05_2cta.cu): tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA loads half of the weight tile.
 int gemm_tc2_init();
 int gemm_tc2_launch(const GemmArgs& g, int num_sms, cudaStream_t stream);

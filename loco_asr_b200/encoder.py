@@ -61,8 +61,34 @@ class _SubmoduleShim:
         return "<All keys matched successfully>"
 
 
+class LocoPlan:
+    """A batch geometry made ready to launch (``loco_plan_create``): encoding with it is a pure enqueue (kernels and memset
+    nodes only), so the call can be captured into a CUDA graph and replayed after refilling the same input buffer."""
+
+    def __init__(self, owner: "LocoSpeechT5Encoder", handle, kind: int, lengths: np.ndarray):
+        self._owner, self._p, self.kind, self.lengths = owner, handle, kind, lengths
+        n = len(lengths)
+        self.frames = np.zeros(n, dtype=np.int32)
+        self.rows = np.zeros(n, dtype=np.int32)
+        total, ws = C.c_int64(), C.c_size_t()
+        rc = owner._lib.loco_plan_info(handle, self.frames.ctypes.data, self.rows.ctypes.data, C.byref(total), C.byref(ws))
+        _lib.check(owner._lib, owner._h, rc, "loco_plan_info")
+        self.total_frames, self.workspace_bytes = int(total.value), int(ws.value)
+
+    def close(self):
+        if self._p is not None and getattr(self._owner, "_h", None):
+            self._owner._lib.loco_plan_destroy(self._owner._h, self._p)
+        self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class LocoSpeechT5Encoder:
-    def __init__(self, config=None, device: "torch.device | str | int" = "cuda:0"):
+    def __init__(self, config=None, device: "torch.device | str | int" = "cuda:0", debug: bool = False):
         self.config = LocoSpeechT5Config.from_hf(config) if config is not None else LocoSpeechT5Config()
         self.config.validate()
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
@@ -71,7 +97,7 @@ class LocoSpeechT5Encoder:
         if not torch.cuda.is_available():
             raise _lib.LocoError("no CUDA device is visible; the B200 extension cannot run and there is no CPU fallback")
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
-        self._lib = _lib.load()
+        self._lib = _lib.load(debug=debug)       # debug: the LOCO_DEBUG build with the cross-check kernels (tests, tools/)
         cc = _lib.LocoConfigC()
         self._lib.loco_default_config(C.byref(cc))
         cc.encoder_layers = self.config.encoder_layers
@@ -111,8 +137,8 @@ class LocoSpeechT5Encoder:
         return "<All keys matched successfully>"
 
     @classmethod
-    def from_state_dict(cls, state_dict, config=None, device="cuda:0") -> "LocoSpeechT5Encoder":
-        enc = cls(config, device)
+    def from_state_dict(cls, state_dict, config=None, device="cuda:0", debug: bool = False) -> "LocoSpeechT5Encoder":
+        enc = cls(config, device, debug=debug)
         enc.load_state_dict(state_dict)
         enc.finalize()
         return enc
@@ -161,8 +187,39 @@ class LocoSpeechT5Encoder:
         if self._workspace is None or self._workspace.numel() < nbytes:
             self._workspace = None
             self._workspace = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=self.device)
-        off = (-self._workspace.data_ptr()) % 1024
-        return self._workspace[off:]
+        return self._workspace       # any alignment: the library rounds the base up itself
+
+    # ------------------------------------------------------------------ plans: pure-enqueue encodes (CUDA-graph capturable)
+    def make_plan(self, lengths: Sequence[int], text: bool = False) -> LocoPlan:
+        """``loco_plan_create`` for one batch geometry (samples per utterance, or tokens per text).  Synchronous; do it
+        outside hot loops and outside stream captures."""
+        self.finalize()
+        ls = np.ascontiguousarray(np.asarray(lengths, dtype=np.int32))
+        p = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self._lib.loco_plan_create(self._h, 1 if text else 0, ls.ctypes.data, int(ls.shape[0]), C.byref(p))
+        _lib.check(self._lib, self._h, rc, "loco_plan_create")
+        return LocoPlan(self, p, 1 if text else 0, ls)
+
+    def encode_planned(self, plan: LocoPlan, inp: torch.Tensor, pooled: torch.Tensor, workspace: torch.Tensor,
+                       hidden: Optional[torch.Tensor] = None):
+        """``loco_encode_planned``: every buffer is the caller's (``inp`` f32 waveforms / i32 tokens [sum lengths], ``pooled``
+        f32 [B, 768], ``workspace`` uint8 [>= plan.workspace_bytes], optional ``hidden`` f32 [plan.total_frames, 768]).
+        Enqueues on the current stream and returns; nothing is allocated, copied from the host or synchronised."""
+        if inp.numel() != int(plan.lengths.sum()) or inp.device != self.device:
+            raise _lib.LocoError("encode_planned: the input does not match the plan")
+        with torch.cuda.device(self.device):
+            rc = self._lib.loco_encode_planned(self._h, plan._p, inp.data_ptr(), pooled.data_ptr(),
+                                               hidden.data_ptr() if hidden is not None else None, workspace.data_ptr(),
+                                               workspace.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(self._lib, self._h, rc, "loco_encode_planned")
+        return pooled
+
+    def sync_check(self):
+        """``loco_sync_check``: synchronise the current stream and raise on any asynchronous CUDA error."""
+        with torch.cuda.device(self.device):
+            rc = self._lib.loco_sync_check(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(self._lib, self._h, rc, "loco_sync_check")
 
     # ------------------------------------------------------------------ var-len fast path (device buffers)
     # ------------------------------------------------------------------ classifier head as the encoder's epilogue

@@ -4,12 +4,15 @@ Same CLI (``-m {audio,text} -s {train,devel,test,train_synthetic}``), same outpu
 (``extracted/{speecht5|speecht5_base}/<split>/<modality>/<slurp_id>_embedding_and_target.pickle`` holding
 ``{"id", "embedding": np.float32[T, 768], "target": one-hot[101]}``, reference :70-77,:111-113) that
 ``slurp_embeddings_and_targets.py:19-28`` and ``train_classifier.py`` read back -- but the loop is restructured
-for throughput: utterances are length-bucketed into padding-free batches of <= 64k frames, encoded by the CUDA
-library, and written by a pool of writer threads; existing files are skipped (resume).
+for throughput: waveforms are decoded by worker threads while the GPU works (nothing is materialised up front), cut into
+padding-free batches of <= 131072 frames, encoded by the CUDA library, and written by a pool of writer threads;
+existing files are skipped (resume).  Under ``torchrun`` every rank takes every world-th utterance and writes its own files.
 
-``embedding`` is the pooled [1, 768] vector by default (3 KB instead of ~460 KB per utterance; ``pad_sequence`` +
-``mean(dim=1)`` / ``max`` / attention pooling in the reference classifier all accept T = 1); ``--full-sequence``
-writes the reference's [T, 768].
+``embedding`` is the reference's [T, 768] ``last_hidden_state`` (the utterance's own T frames) by default, so every pooling
+of ``train_classifier.py`` (average / max / self-attention over frames) sees what it expects.  ``--pooled average|max``
+writes that pooling's [1, 768] vector instead (3 KB instead of ~460 KB per utterance, and the encoder's fused pooling never
+sends the sequence to HBM); such files carry a ``"pooling"`` key and a folder never mixes formats.  A classifier trained on
+pooled files must use the same ``--pooling``: pooling a single already-pooled row again is the identity.
 
 Run from the reference's ``speech_text/`` directory (so ``slurp_data`` / ``intent_classes`` import), or pass
 ``--classes-file`` and ``--synthetic N`` to exercise the pipeline without the SLURP corpus (not available offline).
@@ -134,64 +137,201 @@ def output_path(folder: str, slurp_id) -> str:
     return os.path.join(folder, f"{slurp_id}_embedding_and_target.pickle")
 
 
-def write_item(folder: str, slurp_id, embedding: np.ndarray, target: np.ndarray) -> str:
+def write_item(folder: str, slurp_id, embedding: np.ndarray, target: np.ndarray, pooling: Optional[str] = None) -> str:
+    """One file per utterance, the reference's dict (:111-113).  A pooled file also says which pooling it holds
+    (``"pooling"``; the reference's reader ignores extra keys) so that a classifier is never trained on a mix."""
     path = output_path(folder, slurp_id)
     tmp = path + ".tmp"
-    with open(tmp, "wb") as handle:
-        pickle.dump({"id": slurp_id, "embedding": np.ascontiguousarray(embedding, dtype=np.float32), "target": target},
-                    handle, protocol=pickle.HIGHEST_PROTOCOL)
+    item = {"id": slurp_id, "embedding": np.ascontiguousarray(embedding, dtype=np.float32), "target": target}
+    if pooling:
+        item["pooling"] = pooling
+    blob = pickle.dumps(item, protocol=pickle.HIGHEST_PROTOCOL)
+    fd = os.open(tmp, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        os.write(fd, blob)
+    finally:
+        os.close(fd)
     os.replace(tmp, path)      # a killed run never leaves a half-written file for the resume check to trust
     return path
 
 
+def write_many(folder: str, ids, embeddings, targets, pooling: Optional[str] = None) -> int:
+    """A chunk of files from ONE writer task: per-file Python overhead is what limits the writer (a thread per file fights over the
+    interpreter lock: 2 k files/s from 8 threads, 20 k files/s from one loop), so tasks are per batch, not per utterance."""
+    for k, slurp_id in enumerate(ids):
+        write_item(folder, slurp_id, embeddings[k], targets[k], pooling)
+    return len(ids)
+
+
+class WriterProcs:
+    """Writer PROCESSES fed through pipes (``python -m loco_asr_b200._writer``; numpy only, no CUDA state).  Threads do not work
+    here: every file costs four system calls, each releases the interpreter lock, and with the feeding thread busy each
+    re-acquisition waits for a switch interval -- measured 0.6 ms per open(), 1.9 k files/s, against 20 k files/s for the same
+    loop in a process of its own.  A full pipe blocks ``submit``: that is the back-pressure."""
+
+    def __init__(self, writers: int):
+        import subprocess
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        self.procs = [subprocess.Popen([sys.executable, "-m", "loco_asr_b200._writer"], stdin=subprocess.PIPE, env=env)
+                      for _ in range(max(1, writers))]
+        self.k = 0
+
+    def submit(self, folder, ids, embeddings, targets, pooling=None):
+        import struct
+        blob = pickle.dumps((folder, list(ids), embeddings, list(targets), pooling), protocol=pickle.HIGHEST_PROTOCOL)
+        p = self.procs[self.k % len(self.procs)]
+        self.k += 1
+        p.stdin.write(struct.pack("<Q", len(blob)))
+        p.stdin.write(blob)
+
+    def close(self):
+        rc = 0
+        for p in self.procs:
+            p.stdin.close()
+        for p in self.procs:
+            rc |= p.wait()
+        if rc:
+            raise RuntimeError("an embedding writer process failed; some files were not written")
+
+
+def check_folder_format(folder: str, pooling: Optional[str]):
+    """Refuse to add files of one format to a folder that holds the other: ``train_classifier.py --pooling max|attention``
+    over already-averaged [1, 768] rows runs without error but computes something else than pooling over frames."""
+    if not os.path.isdir(folder):
+        return
+    for name in os.listdir(folder):
+        if not name.endswith("_embedding_and_target.pickle"):
+            continue
+        with open(os.path.join(folder, name), "rb") as fh:
+            have = pickle.load(fh).get("pooling")
+        if have != pooling:
+            raise SystemExit(f"{folder} already holds {'pooled (' + have + ')' if have else 'full-sequence'} files; this run would add "
+                             f"{'pooled (' + pooling + ')' if pooling else 'full-sequence'} ones.  Use another --out-root or the same format.")
+        return
+
+
 # ------------------------------------------------------------------------------------------------ main
-def run(encoder, items, waves_fn, binarize, folder: str, full_sequence: bool = False, max_frames: int = 131072,
-        writers: int = 8, resume: bool = True, log=print):
-    """items: [(slurp_id, key, intent)]; waves_fn(key) -> float32 waveform."""
+def stream_batches(todo, waves_fn, frames_fn, max_frames: int, decoders: int = 8, lookahead: int = 2):
+    """Decode / produce waveforms in worker threads and cut them into padding-free batches as they arrive: yields
+    ``(indices into todo, [waveforms])`` with at most `max_frames` encoder frames.  At most `lookahead` batches' worth of
+    decoded audio is alive at a time (the reference decodes serially inside its collate function, :55-57; materialising a
+    whole split first costs > 10 GB of host memory for SLURP train)."""
+    from collections import deque
+    pool = ThreadPoolExecutor(max_workers=decoders) if decoders > 1 else None   # cheap decoders run inline: threads only add hand-offs
+    pending = deque()
+    it = iter(range(len(todo)))
+    budget = max(64, decoders * 4) if pool else 1
+
+    def refill():
+        while len(pending) < budget:
+            i = next(it, None)
+            if i is None:
+                return
+            pending.append((i, pool.submit(waves_fn, todo[i][1]) if pool else None))
+
+    refill()
+    idx, waves, frames = [], [], 0
+    while pending:
+        i, fut = pending.popleft()
+        w = fut.result() if pool else waves_fn(todo[i][1])
+        refill()
+        f = int(frames_fn(len(w))) + 2
+        if idx and frames + f > max_frames:
+            yield idx, waves
+            idx, waves, frames = [], [], 0
+        idx.append(i)
+        waves.append(w)
+        frames += f
+    if idx:
+        yield idx, waves
+    if pool:
+        pool.shutdown()
+
+
+def run(encoder, items, waves_fn, binarize, folder: str, pooled: Optional[str] = None, max_frames: int = 131072,
+        writers: int = 2, decoders: int = 8, resume: bool = True, rank: int = 0, world: int = 1, log=print):
+    """items: [(slurp_id, key, intent)]; waves_fn(key) -> float32 waveform.  ``pooled``: None writes the reference's
+    ``embedding`` [T, 768] (last_hidden_state of the utterance's own frames); "average" / "max" write the pooled [1, 768]
+    vector (150x smaller; "average" rides the copy-overlapped bulk path).  Under torchrun every rank takes every `world`-th
+    item and writes its own files; no collective is needed because the files are the result."""
     import torch
-    from .buckets import make_batches
+    from .buckets import frames_of
 
     os.makedirs(folder, exist_ok=True)
-    todo = [it for it in items if not (resume and os.path.exists(output_path(folder, it[0])))]
-    if len(todo) < len(items):
-        log(f"resume: {len(items) - len(todo)} of {len(items)} outputs already exist")
+    check_folder_format(folder, pooled)
+    mine = items[rank::world]
+    todo = [it for it in mine if not (resume and os.path.exists(output_path(folder, it[0])))]
+    if len(todo) < len(mine):
+        log(f"resume: {len(mine) - len(todo)} of {len(mine)} outputs already exist")
     if not todo:
         return 0
-    waves = [waves_fn(it[1]) for it in todo]
-    lengths = [len(w) for w in waves]
     targets = binarize([it[2] for it in todo])
-    pool = ThreadPoolExecutor(max_workers=writers)
-    futures = []
-    batches = make_batches(lengths, max_frames=max_frames)
-    if not full_sequence:
-        # pooled output: H2D of the next batch overlaps the encode of the current one (encode_host_pipelined)
+    pool = WriterProcs(writers)
+    cuda = torch.cuda.is_available()
+    def frames_fn(n):        # HF _get_feat_extract_output_lengths in plain integers (numpy costs 70 us per call here)
+        for k, st in ((10, 5), (3, 2), (3, 2), (3, 2), (3, 2), (2, 2), (2, 2)):
+            n = (n - k) // st + 1 if n >= k else 0
+        return n
+    if pooled is None:
+        max_frames = min(max_frames, 32768)      # [sum T, 768] fp32 crosses PCIe and sits in host memory: 100 MB per batch
+
+    def sorted_batches():
+        for idx, waves in stream_batches(todo, waves_fn, frames_fn, max_frames, decoders):
+            order = sorted(range(len(idx)), key=lambda k: len(waves[k]))     # short to long inside the batch: dense tiles
+            yield [idx[k] for k in order], [waves[k] for k in order]
+
+    if pooled == "average":
+        # H2D of the next batch overlaps the encode of the current one (encode_host_pipelined); decode runs ahead in threads
+        metas = []
+        ring = [None] * 4           # pinned staging buffers, reused: a waveform is copied once, straight into pinned memory
+                                    # (concatenate + pin_memory per batch were two more passes over 170 MB and a cudaHostAlloc)
+
         def host_batches():
-            for idx in batches:
-                host = torch.from_numpy(np.concatenate([waves[i] for i in idx]))
-                yield (host.pin_memory() if torch.cuda.is_available() else host, [lengths[i] for i in idx])
-        for idx, pooled in zip(batches, encoder.encode_host_pipelined(host_batches())):
-            pooled = pooled.numpy()
-            for j, i in enumerate(idx):
-                futures.append(pool.submit(write_item, folder, todo[i][0], pooled[j:j + 1].copy(), targets[i]))
-        batches = []
-    for idx in batches:
-        host = torch.from_numpy(np.concatenate([waves[i] for i in idx]))
-        ns = [lengths[i] for i in idx]
-        if full_sequence:
-            pooled, hidden, info = encoder.encode_packed(host.to(encoder.device), ns, return_hidden=True)
-            hidden = hidden.cpu().numpy()
-            off = 0
-            for j, i in enumerate(idx):
-                t = int(info["frames"][j])
-                futures.append(pool.submit(write_item, folder, todo[i][0], hidden[off:off + t].copy(), targets[i]))
-                off += t
-        else:
-            pooled = encoder.encode_host(host.pin_memory() if torch.cuda.is_available() else host, ns).numpy()
-            for j, i in enumerate(idx):
-                futures.append(pool.submit(write_item, folder, todo[i][0], pooled[j:j + 1].copy(), targets[i]))
-    for f in futures:
-        f.result()
-    pool.shutdown()
+            for b, (idx, waves) in enumerate(sorted_batches()):
+                n = sum(len(w) for w in waves)
+                k = b % len(ring)   # batch b - 4 has been encoded and read back by now (results are consumed one batch late)
+                if ring[k] is None or ring[k].numel() < n:
+                    ring[k] = torch.empty(max(n, 1 << 20), dtype=torch.float32)
+                    if cuda:
+                        ring[k] = ring[k].pin_memory()
+                dst = ring[k].numpy()
+                off = 0
+                for w in waves:
+                    dst[off:off + len(w)] = w
+                    off += len(w)
+                metas.append(idx)
+                yield (ring[k][:n], [len(w) for w in waves])
+
+        for b, pooled_host in enumerate(encoder.encode_host_pipelined(host_batches())):
+            arr = pooled_host.numpy().copy()[:, None, :]          # [B, 1, 768]: the pinned buffer goes back to the pipeline
+            idx = metas[b]
+            for c in range(0, len(idx), 512):
+                part = idx[c:c + 512]
+                pool.submit(folder, [todo[i][0] for i in part], arr[c:c + 512], [targets[i] for i in part], "average")
+            metas[b] = None
+    else:
+        if pooled == "max":
+            encoder.set_head(method="max")
+        elif pooled is not None:
+            raise ValueError("pooled must be None, 'average' or 'max' (self_attention pooling needs the trained classifier's q: "
+                             "use full-sequence files or LocoSpeechT5Encoder.set_head)")
+        for idx, waves in sorted_batches():
+            dev_wave = torch.from_numpy(np.concatenate(waves)).to(encoder.device)
+            ns = [len(w) for w in waves]
+            if pooled is None:
+                _, hidden, info = encoder.encode_packed(dev_wave, ns, return_hidden=True)
+                hidden = hidden.cpu().numpy()
+                offs = np.concatenate([[0], np.cumsum(info["frames"])])
+                for c in range(0, len(idx), 64):
+                    part = range(c, min(c + 64, len(idx)))
+                    pool.submit(folder, [todo[idx[j]][0] for j in part], [hidden[offs[j]:offs[j + 1]] for j in part],
+                                [targets[idx[j]] for j in part], None)
+            else:
+                _, head_pooled, _ = encoder.encode_packed(dev_wave, ns, with_head=True)
+                arr = head_pooled.cpu().numpy()[:, None, :]
+                pool.submit(folder, [todo[i][0] for i in idx], arr, [targets[i] for i in idx], "max")
+    pool.close()
     return len(todo)
 
 
@@ -207,13 +347,18 @@ def load_tokenizer(name_or_path: str):
     return lambda sentence: np.asarray(tok(sentence)["input_ids"], dtype=np.int64)
 
 
-def run_text(encoder, items, tokens_fn, binarize, folder: str, full_sequence: bool = False, max_tokens: int = 131072,
-             writers: int = 8, resume: bool = True, log=print):
+def run_text(encoder, items, tokens_fn, binarize, folder: str, pooled: Optional[str] = None, max_tokens: int = 131072,
+             writers: int = 8, resume: bool = True, rank: int = 0, world: int = 1, log=print):
     """Text modality: items [(slurp_id, sentence-key, intent)]; tokens_fn(key) -> int token ids.  Same files as run()."""
     import torch
     from .buckets import make_batches
 
     os.makedirs(folder, exist_ok=True)
+    check_folder_format(folder, pooled)
+    if pooled not in (None, "average"):
+        raise ValueError("text modality: pooled must be None or 'average'")
+    full_sequence = pooled is None
+    items = items[rank::world]
     todo = [it for it in items if not (resume and os.path.exists(output_path(folder, it[0])))]
     if len(todo) < len(items):
         log(f"resume: {len(items) - len(todo)} of {len(items)} outputs already exist")
@@ -222,8 +367,7 @@ def run_text(encoder, items, tokens_fn, binarize, folder: str, full_sequence: bo
     toks = [np.asarray(tokens_fn(it[1]), dtype=np.int64) for it in todo]
     lengths = [len(t) for t in toks]
     targets = binarize([it[2] for it in todo])
-    pool = ThreadPoolExecutor(max_workers=writers)
-    futures = []
+    pool = WriterProcs(writers)
     order = sorted(range(len(todo)), key=lambda i: lengths[i])
     start = 0
     while start < len(order):
@@ -240,15 +384,12 @@ def run_text(encoder, items, tokens_fn, binarize, folder: str, full_sequence: bo
             hidden = hidden.cpu().numpy()
             off = 0
             for j, i in enumerate(idx):
-                futures.append(pool.submit(write_item, folder, todo[i][0], hidden[off:off + nt[j]].copy(), targets[i]))
+                pool.submit(folder, [todo[i][0]], [hidden[off:off + nt[j]]], [targets[i]], None)
                 off += nt[j]
         else:
-            pooled = encoder.encode_text_packed(packed, nt).cpu().numpy()
-            for j, i in enumerate(idx):
-                futures.append(pool.submit(write_item, folder, todo[i][0], pooled[j:j + 1].copy(), targets[i]))
-    for f in futures:
-        f.result()
-    pool.shutdown()
+            arr = encoder.encode_text_packed(packed, nt).cpu().numpy()
+            pool.submit(folder, [todo[i][0] for i in idx], arr[:, None, :], [targets[i] for i in idx], "average")
+    pool.close()
     return len(todo)
 
 
@@ -264,8 +405,16 @@ def main(argv=None):
     p.add_argument("--mapping-dir", default="extracted/speecht5/mapping",
                    help="folder with encoder_state_dict.pickle / speech_prenet_state_dict.pickle (reference :41-49)")
     p.add_argument("--classes-file")
-    p.add_argument("--full-sequence", action="store_true", help="write [T, 768] like the reference instead of pooled [1, 768]")
+    p.add_argument("--pooled", choices=["average", "max"], default=None,
+                   help="write the pooled [1, 768] vector instead of the reference's [T, 768] (recorded in the file as 'pooling')")
+    p.add_argument("--full-sequence", action="store_true", help="(default) write [T, 768] like the reference")
+    p.add_argument("--decoders", type=int, default=8, help="waveform decode threads")
+    p.add_argument("--writers", type=int, default=2, help="pickle writer threads (tasks are whole chunks of files)")
+    p.add_argument("--report", help="write a JSON throughput report of this run (utterances, audio-s, seconds, files) to this path")
     p.add_argument("--synthetic", type=int, default=0, help="use N synthetic SLURP-shaped utterances and random-init weights")
+    p.add_argument("--synthetic-decoder", choices=["synth", "slice"], default="synth",
+                   help="synthetic waveforms: 'synth' = the seeded generator the tests compare against (8 ms of numpy each), "
+                        "'slice' = memcpy-speed windows of one recording (throughput runs: the host pipeline, not numpy, is measured)")
     p.add_argument("--device", default="cuda:0")
     p.add_argument("--max-frames", type=int, default=131072)
     p.add_argument("--do-normalize", action="store_true", help="zero-mean / unit-variance waveforms (the feature extractor's do_normalize)")
@@ -273,8 +422,14 @@ def main(argv=None):
     a = p.parse_args(argv)
     print(f"Extracting {a.modality} embeddings from SLURP {a.split} set using SpeechT5 (loco_asr_b200)")
 
+    import time
     import torch
     from .encoder import LocoSpeechT5Encoder
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:          # torchrun: one process per GPU, each with its own share of the utterances and its own writers
+        a.device = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
+    if a.pooled and a.full_sequence:
+        raise SystemExit("--pooled and --full-sequence exclude each other")
     enc = LocoSpeechT5Encoder(device=a.device)
     text = a.modality == "text"
     if a.synthetic and text:
@@ -292,7 +447,13 @@ def main(argv=None):
         classes = load_classes(a.classes_file) if (a.classes_file or "intent_classes" in sys.modules) else [f"intent_{i:03d}" for i in range(101)]
         lens = slurp_shaped_lengths(a.synthetic, 1234)
         items = [(f"synth{i}", i, classes[i % len(classes)]) for i in range(a.synthetic)]
-        waves_fn = lambda i: synth_wave(int(lens[i]), 1234, int(i))
+        if a.synthetic_decoder == "slice":
+            # stands in for reading decoded PCM: a window of one 11 s recording, scaled -- memcpy-speed, like a warm page cache
+            # (synth_wave itself costs ~8 ms of numpy per utterance, more than the GPU spends on 100 of them)
+            base = synth_wave(176000, 1234, 0)
+            waves_fn = lambda i: base[(int(i) * 7919) % (176000 - int(lens[i]) + 1):][:int(lens[i])] * np.float32(0.5 + 0.001 * (int(i) % 997))
+        else:
+            waves_fn = lambda i: synth_wave(int(lens[i]), 1234, int(i))
     else:
         classes = load_classes(a.classes_file)
         if a.weights:
@@ -311,11 +472,23 @@ def main(argv=None):
     enc.finalize()
     print(f"{a.split} set size: {len(items)}")
     folder = output_folder(a.out_root, a.version, a.split, a.modality)
+    t0 = time.perf_counter()
     if text:
-        n = run_text(enc, items, waves_fn, make_label_binarizer(classes), folder, full_sequence=a.full_sequence, max_tokens=a.max_frames)
+        n = run_text(enc, items, waves_fn, make_label_binarizer(classes), folder, pooled=a.pooled, max_tokens=a.max_frames,
+                     writers=a.writers, rank=rank, world=world)
     else:
-        n = run(enc, items, waves_fn, make_label_binarizer(classes), folder, full_sequence=a.full_sequence, max_frames=a.max_frames)
-    print(f"wrote {n} files\nDone!")
+        n = run(enc, items, waves_fn, make_label_binarizer(classes), folder, pooled=a.pooled, max_frames=a.max_frames,
+                writers=a.writers, decoders=a.decoders, rank=rank, world=world)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"wrote {n} files{'' if world == 1 else f' (rank {rank} of {world})'} in {dt:.1f} s\nDone!")
+    if a.report and not text:
+        audio_s = float(sum(lens[i] for i in range(rank, a.synthetic, world))) / SAMPLE_RATE if a.synthetic else None
+        with open(a.report + (f".rank{rank}" if world > 1 else ""), "w") as fh:
+            json.dump({"files_written": n, "seconds": dt, "utterances_per_s": n / dt if dt > 0 else None, "audio_s": audio_s,
+                       "e2e_files_audio_s_per_s": audio_s / dt if (audio_s and dt > 0 and n) else None, "rank": rank, "world": world,
+                       "format": a.pooled or "full-sequence", "decoders": a.decoders, "writers": a.writers,
+                       "timed": "decode/synthesis + H2D + encode + D2H + one pickle per utterance on disk (wall clock)"}, fh)
 
 
 if __name__ == "__main__":

@@ -25,3 +25,13 @@ def encoder(weights):
     from loco_asr_b200.encoder import LocoSpeechT5Encoder
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     return LocoSpeechT5Encoder.from_state_dict(weights, device="cuda:0")
+
+
+@pytest.fixture(scope="session")
+def debug_encoder(weights):
+    """The LOCO_DEBUG build (libloco_asr_debug.so): the product kernels plus the cross-check kernels and the knobs that select
+    them (loco_debug_set).  Only the tests that switch kernels or stop after a layer use it; parity tests run on `encoder`."""
+    import torch
+    from loco_asr_b200.encoder import LocoSpeechT5Encoder
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return LocoSpeechT5Encoder.from_state_dict(weights, device="cuda:0", debug=True)

@@ -29,7 +29,31 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/loco_asr.h but not exported"
     assert set(declared_symbols()) == set(_lib.SIGNATURES), "ctypes binding and header drifted"
-    assert _lib.load().loco_abi_version() == 1
+    assert _lib.load().loco_abi_version() == _lib.ABI_VERSION == 2
+    for s in ("loco_plan_create", "loco_encode_planned", "loco_plan_destroy", "loco_sync_check"):
+        assert s in declared_symbols()
+
+
+def test_product_library_ships_only_product_kernels():
+    """The cross-check kernels (SIMT GEMM, single-CTA tcgen05 GEMM, mma.sync positional conv and attention) live only in the
+    LOCO_DEBUG twin; the product library's device code does not contain them, and its attention path has no mma.sync."""
+    import subprocess
+    assert os.path.exists(_lib.DEBUG_LIB_PATH)
+    assert _lib.load().loco_is_debug_build() == 0 and _lib.load(debug=True).loco_is_debug_build() == 1
+
+    def kernels(path):
+        out = subprocess.run(["cuobjdump", "-elf", path], capture_output=True, text=True).stdout
+        return set(re.findall(r"\.text\.(\w+)", out))
+
+    prod, dbg = kernels(_lib.LIB_PATH), kernels(_lib.DEBUG_LIB_PATH)
+    if not prod:
+        pytest.skip("cuobjdump not available")
+    joined = " ".join(sorted(prod))
+    for name in ("gemm_simt", "gemm_tc_kernel", "posconv_kernel", "attention_kernel"):
+        assert not re.search(r"\d+%s" % name, joined), name
+        assert re.search(r"\d+%s" % name, " ".join(sorted(dbg))), name
+    for name in ("gemm_tc2_kernel", "attention_tc_kernel", "posconv_tc_kernel", "conv0_mma_kernel", "final_ln_pool_kernel"):
+        assert re.search(name, joined), name
 
 
 def test_default_config_struct_matches_python_config():

@@ -42,16 +42,16 @@ def _make(M, N, K, epi, conv_like, seed):
 
 @pytest.mark.parametrize("impl", [2, 0], ids=["cta_pair", "single_cta"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"M{c[0]}_N{c[1]}_K{c[2]}_e{c[3]}{'_conv' if c[4] else ''}")
-def test_tcgen05_gemm_matches_fp32_reference(encoder, case, impl):
+def test_tcgen05_gemm_matches_fp32_reference(debug_encoder, case, impl):
     """Both tcgen05 kernels: the CTA-pair product path (cta_group::2, 256 x 256 tiles) and the single-CTA kernel."""
     M, N, K, epi, conv_like = case
     a, lda, w, bias, res, ref = _make(M, N, K, epi, conv_like, seed=M + N + K)
-    c = encoder.debug_gemm(a, w, bias=bias, residual=res, epilogue=epi, impl=impl, lda=lda, m=M)
+    c = debug_encoder.debug_gemm(a, w, bias=bias, residual=res, epilogue=epi, impl=impl, lda=lda, m=M)
     torch.cuda.synchronize()
     err = (c.float() - ref).abs()
     tol = ref.abs() * 2 ** -8 + 2e-3            # bf16 output rounding (+ accumulation-order slack)
     assert bool((err <= tol).all()), f"max err {float(err.max())} at ref {float(ref.flatten()[err.argmax()])}"
-    c2 = encoder.debug_gemm(a, w, bias=bias, residual=res, epilogue=epi, impl=1, lda=lda, m=M)
+    c2 = debug_encoder.debug_gemm(a, w, bias=bias, residual=res, epilogue=epi, impl=1, lda=lda, m=M)
     assert float((c.float() - c2.float()).abs().max()) <= float(ref.abs().max()) * 2 ** -7 + 2e-3
 
 

@@ -22,29 +22,29 @@ STAGE_REL_MAX = 4e-2
 
 
 @pytest.mark.parametrize("ln_impl", [0, 1], ids=["deferred_ln", "ln_kernels"])
-def test_stage_by_stage_against_oracle_taps(encoder, weights, ln_impl):
+def test_stage_by_stage_against_oracle_taps(debug_encoder, weights, ln_impl):
     """Every stage buffer of the first layer against the oracle's taps (isolates a broken kernel).  With the default deferred
     LayerNorm the post-attention LayerNorm never exists as a tensor: the un-normalised sum the out_proj GEMM wrote
     ("attn_res") is normalised here, and the row statistics its epilogue produced are checked against the tensor itself."""
     waves = H.make_waves([6400, 20800, 48000, 9000, 33000])
-    encoder.debug_set("stop_after_layer", 0)
-    encoder.debug_set("ln_impl", ln_impl)
+    debug_encoder.debug_set("stop_after_layer", 0)
+    debug_encoder.debug_set("ln_impl", ln_impl)
     try:
         taps = H.oracle_taps(weights, waves, n_layers=1)
-        pooled, hidden, info = H.run_encoder(encoder, waves)
-        worst = H.compare_stages(encoder, info, taps, H.STAGES, lambda s: None)
+        pooled, hidden, info = H.run_encoder(debug_encoder, waves)
+        worst = H.compare_stages(debug_encoder, info, taps, H.STAGES, lambda s: None)
         layer0 = [(a, b, None) for a, b in H.LAYER0_STAGES if ln_impl == 1 or a != "ln1"]
-        worst.update(H.compare_stages(encoder, info, taps, layer0, lambda s: None))
+        worst.update(H.compare_stages(debug_encoder, info, taps, layer0, lambda s: None))
         if ln_impl == 0:
-            u1 = encoder.debug_buffer("attn_res").float().cpu()
+            u1 = debug_encoder.debug_buffer("attn_res").float().cpu()
             g, b = weights["wrapped_encoder.layers.0.layer_norm.weight"], weights["wrapped_encoder.layers.0.layer_norm.bias"]
             for u, t in enumerate(taps):
                 r0, T = int(info["rows"][u]), t["l0_ln1"].shape[0]
                 got = torch.nn.functional.layer_norm(u1[r0:r0 + T], (768,), g, b, 1e-5)
                 worst["ln1(attn_res)"] = max(worst.get("ln1(attn_res)", 0.0), H.rel_err(got, t["l0_ln1"]))
     finally:
-        encoder.debug_set("stop_after_layer", -1)
-        encoder.debug_set("ln_impl", 0)
+        debug_encoder.debug_set("stop_after_layer", -1)
+        debug_encoder.debug_set("ln_impl", 0)
     assert all(v < STAGE_REL_MAX for v in worst.values()), worst
     off = 0
     for t in taps:
@@ -53,16 +53,16 @@ def test_stage_by_stage_against_oracle_taps(encoder, weights, ln_impl):
         off += T
 
 
-def test_deferred_layernorm_equals_layernorm_kernels(encoder):
+def test_deferred_layernorm_equals_layernorm_kernels(debug_encoder):
     """The two formulations of the post-LN blocks (LayerNorm deferred into the GEMM epilogues, default; LayerNorm kernels)
     on a ragged batch: same function, different rounding points -- last_hidden_state within bf16 noise of each other."""
     waves = H.make_waves([400, 9000, 33000, 64000, 100000], seed=41)
-    p0, h0, _ = H.run_encoder(encoder, waves)
-    encoder.debug_set("ln_impl", 1)
+    p0, h0, _ = H.run_encoder(debug_encoder, waves)
+    debug_encoder.debug_set("ln_impl", 1)
     try:
-        p1, h1, _ = H.run_encoder(encoder, waves)
+        p1, h1, _ = H.run_encoder(debug_encoder, waves)
     finally:
-        encoder.debug_set("ln_impl", 0)
+        debug_encoder.debug_set("ln_impl", 0)
     assert not torch.equal(h0, h1)                      # the knob does select another path
     assert H.rel_err(h0, h1) < 3e-2 and H.rel_err(p0, p1) < 3e-2      # (a 1-frame utterance is in the batch: pooled == its only frame)
     assert float(torch.nn.functional.cosine_similarity(p0, p1, dim=1).min()) > 0.9995
@@ -220,7 +220,7 @@ def test_extract_cli_writes_reference_format_and_head_argmax_matches(tmp_path, c
     from loco_asr_b200.head import IntentHead
     from loco_asr_b200.synth import slurp_shaped_lengths, synth_state_dict
     n = 12
-    extract.main(["-m", "audio", "-s", "test", "--synthetic", str(n), "--out-root", str(tmp_path)])
+    extract.main(["-m", "audio", "-s", "test", "--synthetic", str(n), "--out-root", str(tmp_path), "--pooled", "average"])
     folder = extract.output_folder(str(tmp_path), "base", "test", "audio")
     files = sorted(os.listdir(folder))
     assert len(files) == n and all(f.endswith("_embedding_and_target.pickle") for f in files)
@@ -232,34 +232,47 @@ def test_extract_cli_writes_reference_format_and_head_argmax_matches(tmp_path, c
         with open(extract.output_path(folder, f"synth{i}"), "rb") as fh:
             d = pickle.load(fh)
         assert d["id"] == f"synth{i}" and d["embedding"].dtype == np.float32 and d["embedding"].shape == (1, 768)
-        assert d["target"].shape == (101,) and d["target"].sum() == 1
+        assert d["target"].shape == (101,) and d["target"].sum() == 1 and d["pooling"] == "average"
         ref = O.encode_utterance(sd, torch.from_numpy(synth_wave(int(lens[i]), 1234, i))).mean(0)
         got = torch.from_numpy(d["embedding"])[0]
         assert H.cosine(got, ref) >= COS_MIN
         assert int(head.predict(got[None])) == int(head.predict(ref[None]))
     # resume: nothing left to do
-    extract.main(["-m", "audio", "-s", "test", "--synthetic", str(n), "--out-root", str(tmp_path)])
+    extract.main(["-m", "audio", "-s", "test", "--synthetic", str(n), "--out-root", str(tmp_path), "--pooled", "average"])
     assert "wrote 0 files" in capsys.readouterr().out
-    # the reference's [T, 768] layout on request
-    extract.main(["-m", "audio", "-s", "devel", "--synthetic", "3", "--out-root", str(tmp_path), "--full-sequence"])
+    # a folder never mixes formats: full-sequence files may not be added to the pooled ones
+    with pytest.raises(SystemExit):
+        extract.main(["-m", "audio", "-s", "test", "--synthetic", str(n + 2), "--out-root", str(tmp_path)])
+    # the default is the reference's [T, 768] layout: last_hidden_state of the utterance's own frames, nothing else in the dict
+    extract.main(["-m", "audio", "-s", "devel", "--synthetic", "3", "--out-root", str(tmp_path)])
     with open(extract.output_path(extract.output_folder(str(tmp_path), "base", "devel", "audio"), "synth1"), "rb") as fh:
         d = pickle.load(fh)
-    assert d["embedding"].shape == (O.frame_lengths(int(slurp_shaped_lengths(3, 1234)[1]))[-1], 768)
+    assert set(d) == {"id", "embedding", "target"}
+    T1 = O.frame_lengths(int(slurp_shaped_lengths(3, 1234)[1]))[-1]
+    assert d["embedding"].shape == (T1, 768)
+    ref_seq = O.encode_utterance(sd, torch.from_numpy(synth_wave(int(slurp_shaped_lengths(3, 1234)[1]), 1234, 1)))
+    assert H.cosine(torch.from_numpy(d["embedding"]).mean(0), ref_seq.mean(0)) >= COS_MIN
+    # max pooling over the utterance's own frames through the fused head
+    extract.main(["-m", "audio", "-s", "train", "--synthetic", "3", "--out-root", str(tmp_path), "--pooled", "max"])
+    with open(extract.output_path(extract.output_folder(str(tmp_path), "base", "train", "audio"), "synth1"), "rb") as fh:
+        dm = pickle.load(fh)
+    assert dm["pooling"] == "max" and dm["embedding"].shape == (1, 768)
+    assert float((torch.from_numpy(dm["embedding"])[0] - torch.from_numpy(d["embedding"]).max(0).values).abs().max()) < 1e-5
 
 
 @pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma_sync"])
-def test_attention_kernels_against_oracle(encoder, weights, impl):
+def test_attention_kernels_against_oracle(debug_encoder, weights, impl):
     """Both attention kernels (tcgen05/TMEM product path and the mma.sync cross-check) on a ragged batch whose lengths
     hit: a single frame, < 1 key block, exactly 128 / 129 frames, > 160 (table clamps), several key blocks."""
     lengths = [400, 6400, 41200, 41520, 64000, 100000, 250000]     # T = 1, 19, 128, 129, 199, 312, 781
     waves = H.make_waves(lengths, seed=17)
-    encoder.debug_set("stop_after_layer", 0)
-    encoder.debug_set("attn_impl", impl)
+    debug_encoder.debug_set("stop_after_layer", 0)
+    debug_encoder.debug_set("attn_impl", impl)
     try:
         taps = H.oracle_taps(weights, waves, n_layers=1)
-        pooled, hidden, info = H.run_encoder(encoder, waves)
+        pooled, hidden, info = H.run_encoder(debug_encoder, waves)
         assert info["frames"].tolist() == [1, 19, 128, 129, 199, 312, 781]
-        ctx = encoder.debug_buffer("ctx").float().cpu()
+        ctx = debug_encoder.debug_buffer("ctx").float().cpu()
         for u, t in enumerate(taps):
             r0 = int(info["rows"][u])
             ref = t["l0_ctx"]
@@ -267,8 +280,8 @@ def test_attention_kernels_against_oracle(encoder, weights, impl):
             assert torch.isfinite(got).all(), (impl, u)
             assert H.rel_err(got, ref) < STAGE_REL_MAX, (impl, u, H.rel_err(got, ref))
     finally:
-        encoder.debug_set("stop_after_layer", -1)
-        encoder.debug_set("attn_impl", -1)
+        debug_encoder.debug_set("stop_after_layer", -1)
+        debug_encoder.debug_set("attn_impl", -1)
 
 
 def test_pipelined_host_path_equals_device_path(encoder):
@@ -374,8 +387,11 @@ def test_parity_with_large_layernorm_affines_and_biases(weights):
         assert H.rel_err(pooled[u], ref.mean(0)) < POOLED_REL_MAX, u
         assert H.rel_err(hidden[off:off + T], ref) < 5e-2, u
         off += T
-    enc.debug_set("ln_impl", 1)
-    p1, h1, _ = H.run_encoder(enc, waves)
+    dbg = LocoSpeechT5Encoder.from_state_dict(sd, device="cuda:0", debug=True)      # the LayerNorm-kernel path as a cross-check
+    p0, h0, _ = H.run_encoder(dbg, waves)
+    assert torch.equal(p0, pooled) and torch.equal(h0, hidden)                      # same product kernels in both builds
+    dbg.debug_set("ln_impl", 1)
+    p1, h1, _ = H.run_encoder(dbg, waves)
     assert H.rel_err(hidden, h1) < 3e-2
 
 
@@ -522,3 +538,53 @@ def test_twenty_thousand_tiny_utterances_in_one_launch(encoder):
     for u in (0, 1, 9999, 19998, 19999):
         alone = encoder.encode_packed(wave[int(offs[u]):int(offs[u + 1])].contiguous(), [lengths[u]])
         assert torch.equal(alone[0], pooled[u]), u
+
+
+def test_product_library_has_no_debug_knobs(encoder):
+    from loco_asr_b200._lib import LocoError
+    assert encoder._lib.loco_is_debug_build() == 0
+    with pytest.raises(LocoError):
+        encoder.debug_set("attn_impl", 1)
+    with pytest.raises(LocoError):
+        encoder.debug_set("stop_after_layer", 0)
+
+
+def test_planned_encode_is_graph_capturable_and_replays_on_new_waveforms(encoder):
+    """'all work is enqueued on the caller's stream, no hidden syncs, CUDA-graph-capturable'.  One bucket is
+    planned (loco_plan_create), its encode captured into a CUDA graph (kernels and memset nodes only), and the graph replayed
+    after refilling the same input buffer with other waveforms: bit-identical to the eager call on those waveforms."""
+    lengths = [16000, 23456, 41200, 64000, 99999, 12345]
+    plan = encoder.make_plan(lengths)
+    assert plan.frames.tolist() == [int(O.frame_lengths(n)[-1]) for n in lengths]
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    wave_a = torch.randn(sum(lengths), device="cuda", generator=gen) * 0.1
+    wave_b = torch.randn(sum(lengths), device="cuda", generator=gen) * 0.1
+    want_a = encoder.encode_packed(wave_a, lengths).clone()
+    want_b = encoder.encode_packed(wave_b, lengths).clone()
+    buf = wave_a.clone()
+    pooled = torch.zeros(len(lengths), 768, device="cuda")
+    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device="cuda")
+    encoder.encode_planned(plan, buf, pooled, ws)            # eager, caller-owned buffers
+    encoder.sync_check()
+    assert torch.equal(pooled, want_a)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        pooled.zero_()
+        with torch.cuda.graph(graph, stream=side):
+            encoder.encode_planned(plan, buf, pooled, ws)    # a host sync, cudaMalloc or pageable copy in here would fail the capture
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(pooled, want_a)
+    buf.copy_(wave_b)
+    pooled.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(pooled, want_b)
+    n0 = encoder.launch_count
+    graph.replay()                                            # replays launch no host-side work at all
+    torch.cuda.synchronize()
+    assert encoder.launch_count == n0
+    plan.close()

@@ -151,7 +151,7 @@ def test_extract_cli_text_modality_writes_reference_format(tmp_path, capsys):
     text branch writes (:79-93), readable the way slurp_embeddings_and_targets.py:19-28 reads them."""
     import pickle
     from loco_asr_b200 import extract
-    extract.main(["-m", "text", "-s", "devel", "--synthetic", "5", "--out-root", str(tmp_path), "--full-sequence"])
+    extract.main(["-m", "text", "-s", "devel", "--synthetic", "5", "--out-root", str(tmp_path)])
     folder = extract.output_folder(str(tmp_path), "base", "devel", "text")
     files = sorted(os.listdir(folder))
     assert files == [f"synth{i}_embedding_and_target.pickle" for i in range(5)]

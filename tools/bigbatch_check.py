@@ -6,7 +6,7 @@ import numpy as np, torch
 from loco_asr_b200.encoder import LocoSpeechT5Encoder
 from loco_asr_b200.synth import synth_state_dict
 
-enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=0), device="cuda:0")
+enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=0), device="cuda:0", debug=True)
 for key, val in [a.split("=") for a in sys.argv[2:]]:
     enc.debug_set(key, int(val))
 for max_frames in [int(x) for x in sys.argv[1].split(",")]:

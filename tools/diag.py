@@ -77,7 +77,7 @@ def phase_pipeline(impl, n_layers_stop):
     from loco_asr_b200.encoder import LocoSpeechT5Encoder
     from loco_asr_b200.synth import synth_state_dict
     sd = synth_state_dict(seed=0)
-    enc = LocoSpeechT5Encoder.from_state_dict(sd, device="cuda:0")
+    enc = LocoSpeechT5Encoder.from_state_dict(sd, device="cuda:0", debug=True)
     enc.debug_set("gemm_impl", impl)
     lengths = [6400, 20800, 48000, 9000, 33000]
     waves = H.make_waves(lengths)

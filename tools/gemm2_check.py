@@ -8,7 +8,7 @@ from loco_asr_b200 import _lib
 from loco_asr_b200.encoder import LocoSpeechT5Encoder
 from loco_asr_b200.synth import synth_state_dict
 
-enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device="cuda:0")
+enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device="cuda:0", debug=True)
 g = torch.Generator(device="cuda").manual_seed(0)
 for M, N, K, epi in [(256, 256, 64, _lib.EPI_BIAS), (129, 512, 128, _lib.EPI_BIAS), (1000, 2304, 768, _lib.EPI_BIAS),
                      (777, 3072, 768, _lib.EPI_BIAS_GELU), (640, 768, 3072, _lib.EPI_BIAS_RESIDUAL), (40000, 768, 768, _lib.EPI_BIAS_RESIDUAL)]:

@@ -8,7 +8,7 @@ from loco_asr_b200 import _lib
 from loco_asr_b200.encoder import LocoSpeechT5Encoder
 from loco_asr_b200.synth import synth_state_dict
 
-enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device="cuda:0")
+enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device="cuda:0", debug=True)
 IMPL = int(os.environ.get("GEMM_IMPL", "0"))      # 0 = tcgen05 single-CTA, 2 = CTA-pair (cta_group::2)
 R = 64400
 SHAPES = [  # name, M, N, K, epilogue, conv-like
