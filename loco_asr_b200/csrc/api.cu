@@ -1,6 +1,7 @@
 // C ABI (include/loco_asr.h): handle, checkpoint ingestion, batch geometry and the encoder schedule.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -68,11 +69,12 @@ struct loco_batch_plan {
     int kind = 0;                               // 0 speech (lengths = samples), 1 text (lengths = tokens)
     std::vector<int32_t> lengths;
     Layout L;
-    std::vector<PcTile> at_tiles;               // tcgen05 attention work list (128-query tiles)
+    std::vector<PcTile> at_tiles;               // one-item tcgen05 kernel: 128-query tiles of the utterances routed to it
+    std::vector<PcTile> at_tiles64;             // two-pipeline tcgen05 kernel: 64-query tiles of the utterances routed to it
     std::vector<int32_t> at_utts;               // LOCO_DEBUG builds: utterances routed to the mma.sync cross-check kernel
     int at_ms_max_t6 = 0;
     uint8_t* dev = nullptr;                     // [meta | pc_tiles | at_tiles | at_utts]
-    size_t d_meta = 0, d_pctiles = 0, d_attiles = 0, d_atutts = 0, dev_bytes = 0;
+    size_t d_meta = 0, d_pctiles = 0, d_attiles = 0, d_attiles64 = 0, d_atutts = 0, dev_bytes = 0;
     int device = 0;
     bool cached = false;                        // owned by the handle's plan cache (loco_encode), not by the caller
     uint64_t knobs = 0;                         // debug-knob state the work lists were built under
@@ -114,6 +116,8 @@ struct loco_handle {
     int posconv_impl = 0;
     int ln_impl = 0;            // 0 = LayerNorms of the transformer layers deferred into the GEMM epilogues [default], 1 = LayerNorm kernels
     int attn_impl = 0;          // 0 = tcgen05 [default, the only product kernel], 1 = mma.sync cross-check, -1 = by length (round-1 routing)
+    bool attn_p2 = true;        // utterances shorter than attn_p2_max_frames go to the two-pipeline tcgen05 kernel (attention_p2.cu),
+    int attn_p2_max_frames = 224;   // the others to the one-item-per-SM tcgen05 kernel (attention_tc.cu)
     int attn_tc_min_frames = 193;   // utterances with at least this many frames use the tcgen05 attention kernel,
     int attn_tc_lo = 76, attn_tc_hi = 128;   // ... and so do utterances that fill most of one 128-query tile (see loco_encode)
     alignas(64) CUtensorMap pe_map;   // pe_k [320, 64] for the tcgen05 attention kernel
@@ -585,9 +589,11 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
     h->cfg = *cfg;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("LOCO_ATTN_P2_MAX_FRAMES")) h->attn_p2_max_frames = atoi(e);     // A/B runs (tools/): 0 = one-item kernel only
     int rc = tensormap_init();
     if (!rc) rc = gemm_tc2_init();
     if (!rc) rc = attention_tc_init();
+    if (!rc) rc = attention_p2_init();
     if (!rc) rc = posconv_tc_init();
     if (!rc) rc = frontend_init();
 #ifdef LOCO_DEBUG
@@ -831,7 +837,7 @@ static int finalize_impl(loco_handle* h) {
 namespace {
 
 uint64_t knob_state(const loco_handle* h) {
-    return ((uint64_t)(uint32_t)(h->attn_impl + 1) << 48) ^ ((uint64_t)(uint32_t)h->attn_tc_min_frames << 32) ^
+    return ((uint64_t)(h->attn_p2 ? 1 : 0) << 60) ^ ((uint64_t)(uint32_t)h->attn_p2_max_frames << 20) ^ ((uint64_t)(uint32_t)(h->attn_impl + 1) << 48) ^ ((uint64_t)(uint32_t)h->attn_tc_min_frames << 32) ^
            ((uint64_t)(uint32_t)h->attn_tc_lo << 16) ^ (uint64_t)(uint32_t)h->attn_tc_hi;
 }
 
@@ -878,7 +884,13 @@ int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loc
         tc = h->attn_impl == 0 || (h->attn_impl < 0 && (t6 >= h->attn_tc_min_frames || (t6 >= h->attn_tc_lo && t6 <= h->attn_tc_hi)));
 #endif
         if (tc) {
-            for (int f = 0; f < t6; f += 128) p->at_tiles.push_back({L.meta[u].row6 + f, f, t6, 0});
+            // Which tcgen05 kernel: by the utterance's OWN frame count (never by its batch-mates, so its result does not depend
+            // on the batch it travels in).  tools/attn_sweep.py, ms per layer at 64k frames, two-pipeline / one-item: 64 frames
+            // 0.15 / 0.38, 128: 0.21 / 0.26, 149: 0.32 / 0.56, 192: 0.29 / 0.50, 256: 0.36 / 0.33, 499: 0.57 / 0.49, 2999: 2.1 / 1.6.
+            if (h->attn_p2 && t6 < h->attn_p2_max_frames)
+                for (int f = 0; f < t6; f += 64) p->at_tiles64.push_back({L.meta[u].row6 + f, f, t6, 0});
+            else
+                for (int f = 0; f < t6; f += 128) p->at_tiles.push_back({L.meta[u].row6 + f, f, t6, 0});
         } else {
             p->at_utts.push_back(u);
             if (t6 > p->at_ms_max_t6) p->at_ms_max_t6 = t6;
@@ -910,6 +922,7 @@ int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loc
     p->d_meta = place((size_t)n_utts * sizeof(UttMeta));
     p->d_pctiles = place(L.pc_tiles.size() * sizeof(PcTile));
     p->d_attiles = place(p->at_tiles.size() * sizeof(PcTile));
+    p->d_attiles64 = place(p->at_tiles64.size() * sizeof(PcTile));
     p->d_atutts = place(p->at_utts.size() * sizeof(int32_t));
     if (p->dev_bytes == 0) p->dev_bytes = 256;
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->dev), p->dev_bytes);
@@ -919,6 +932,7 @@ int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loc
     up(p->d_meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta));
     up(p->d_pctiles, L.pc_tiles.data(), L.pc_tiles.size() * sizeof(PcTile));
     up(p->d_attiles, p->at_tiles.data(), p->at_tiles.size() * sizeof(PcTile));
+    up(p->d_attiles64, p->at_tiles64.data(), p->at_tiles64.size() * sizeof(PcTile));
     up(p->d_atutts, p->at_utts.data(), p->at_utts.size() * sizeof(int32_t));
     if (e != cudaSuccess) {
         free_plan(p);
@@ -983,6 +997,7 @@ static int run_transformer(loco_handle* h, const loco_batch_plan& P, uint8_t* ws
     const UttMeta* meta = reinterpret_cast<const UttMeta*>(P.dev + P.d_meta);
     const int R6 = (int)L.R6;
     const PcTile* at_tiles_dev = reinterpret_cast<const PcTile*>(P.dev + P.d_attiles);
+    const PcTile* at_tiles64_dev = reinterpret_cast<const PcTile*>(P.dev + P.d_attiles64);
     const int32_t* at_utts_dev = reinterpret_cast<const int32_t*>(P.dev + P.d_atutts);
     (void)at_utts_dev;
     // slot padding rows of ctx are never written by the attention kernels; keep them finite (zero) so they stay finite
@@ -1019,6 +1034,8 @@ static int run_transformer(loco_handle* h, const loco_batch_plan& P, uint8_t* ws
         if (!P.at_utts.empty())
             LAUNCH(CAT_ATTENTION, launch_attention(B("qkv"), h->pe_k, meta, at_utts_dev, (int)P.at_utts.size(), P.at_ms_max_t6, B("ctx"), s), 1);
 #endif
+        if (!P.at_tiles64.empty())
+            LAUNCH(CAT_ATTENTION, launch_attention_p2(&qkv_map, &h->pe_map, at_tiles64_dev, (int)P.at_tiles64.size(), B("ctx"), h->num_sms, s), 1);
         if (!P.at_tiles.empty())
             LAUNCH(CAT_ATTENTION, launch_attention_tc(&qkv_map, &h->pe_map, at_tiles_dev, (int)P.at_tiles.size(), B("ctx"), h->num_sms, s), 1);
         g = GemmArgs();
@@ -1374,6 +1391,8 @@ int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
     else if (!strcmp(name, "posconv_impl")) h->posconv_impl = (int)value;
     else if (!strcmp(name, "ln_impl")) h->ln_impl = (int)value;
     else if (!strcmp(name, "attn_impl")) h->attn_impl = (int)value;
+    else if (!strcmp(name, "attn_p2")) h->attn_p2 = value != 0;
+    else if (!strcmp(name, "attn_p2_max_frames")) h->attn_p2_max_frames = (int)value;
     else if (!strcmp(name, "attn_tc_min_frames")) h->attn_tc_min_frames = (int)value;
     else if (!strcmp(name, "attn_tc_lo")) h->attn_tc_lo = (int)value;
     else if (!strcmp(name, "attn_tc_hi")) h->attn_tc_hi = (int)value;

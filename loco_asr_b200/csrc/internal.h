@@ -151,6 +151,11 @@ int attention_init();
 int attention_tc_init();
 int launch_attention_tc(const void* qkv_map /*CUtensorMap*/, const void* pe_map /*CUtensorMap*/, const PcTile* tiles, int n_tiles,
                         bf16* ctx /*[R6, 768]*/, int num_sms, cudaStream_t s);
+// Two-pipeline variant (attention_p2.cu): two (64-query tile, head) items per SM at a time, each in its own half of the TMEM
+// lanes.  `tiles`: 64-frame tiles of every utterance.
+int attention_p2_init();
+int launch_attention_p2(const void* qkv_map /*CUtensorMap*/, const void* pe_map /*CUtensorMap*/, const PcTile* tiles, int n_tiles,
+                        bf16* ctx /*[R6, 768]*/, int num_sms, cudaStream_t s);
 // utt_index: the utterances to process (indices into meta), or nullptr for all of 0..n_utts-1
 int launch_attention(const bf16* qkv /*[R6, 2304]*/, const bf16* pe_k /*[320, 64]*/, const UttMeta* meta, const int32_t* utt_index,
                      int n_utts, int max_t6, bf16* ctx /*[R6, 768]*/, cudaStream_t s);

@@ -10,8 +10,8 @@ Fixtures
                    SpeechT5EncoderWithTextPrenet, weights seed 0 + text prenet seed 0: pooled, first / last token rows.
   config5_hf.npz   BASELINE.json configs[4] / SURVEY.md 8(d) "Config 5": a fixed 512-utterance subset (every ~137th) of the
                    70k SLURP-shaped set (lengths seed 1234, weights seed 1, waveform seed 1234): the HF module's pooled embedding
-                   (stored fp16), and logits / argmax of IntentClassifier(average) with the seed-3 random Linear(768,101)
-                   computed from the fp32 pooled vector.   ``python -m oracle.make_golden --config5-only``
+                   (fp32), logits / argmax / top-2 margin of IntentClassifier(average) with the seed-3 random Linear(768,101), and
+                   what the same module does under bf16 autocast (argmax, rel err, cosine).   ``python -m oracle.make_golden --config5-only``
   long60_hf.npz    BASELINE.json configs[3]: one 60 s segment (T = 2999; the HF module materialises 2.3 GB of position_bias for it),
                    weights seed 0, waveform seed 21: pooled, and 16 evenly spaced rows of last_hidden_state.
                    ``python -m oracle.make_golden --long60-only``
@@ -70,23 +70,34 @@ def config5_ids(n_total: int = 70000, n: int = 512):
 
 
 def make_config5(out_dir):
+    """Also runs the SAME unmodified HF module under torch.autocast(bfloat16) -- the reference's own arithmetic at the CUDA path's
+    operand precision (bf16 GEMM / conv operands, fp32 softmax / LayerNorm) -- and stores what that alone does to the pooled
+    embedding and to the intent argmax: the yardstick for the CUDA path's bf16 error (tests/test_gpu_parity.py)."""
     from loco_asr_b200.synth import slurp_shaped_lengths, synth_head
     lengths = slurp_shaped_lengths(70000, 1234)
     ids = config5_ids()
     model = build_hf_encoder(synth_state_dict(seed=1))
     w, b = synth_head(3)
-    pooled = []
+    pooled, pooled16 = [], []
     for k in range(0, len(ids), 16):
         waves = [synth_wave(int(lengths[i]), 1234, int(i)) for i in ids[k:k + 16]]
         pooled += [h.mean(0) for h in hf_encode_unpadded(model, waves)]
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            pooled16 += [h.float().mean(0) for h in hf_encode_unpadded(model, waves)]
         print(f"config5: {k + 16}/{len(ids)}", flush=True)
-    pooled = torch.stack(pooled)
+    pooled, pooled16 = torch.stack(pooled), torch.stack(pooled16)
     logits = torch.nn.functional.linear(pooled, w, b)
+    logits16 = torch.nn.functional.linear(pooled16, w, b)
     top2 = logits.topk(2, dim=1).values
     np.savez_compressed(os.path.join(out_dir, "config5_hf.npz"), ids=ids, n_samples=lengths[ids].astype(np.int64),
-                        pooled_f16=pooled.numpy().astype(np.float16), logits=logits.numpy().astype(np.float32),
+                        pooled=pooled.numpy().astype(np.float32), logits=logits.numpy().astype(np.float32),
                         argmax=logits.argmax(dim=1).numpy().astype(np.int64),
-                        margin=(top2[:, 0] - top2[:, 1]).numpy().astype(np.float32), weights_seed=1, wave_seed=1234, head_seed=3)
+                        margin=(top2[:, 0] - top2[:, 1]).numpy().astype(np.float32),
+                        hf_bf16_argmax=logits16.argmax(dim=1).numpy().astype(np.int64),
+                        hf_bf16_rel_err=((pooled16 - pooled).abs().amax(1) / pooled.abs().amax(1)).numpy().astype(np.float32),
+                        hf_bf16_cosine=torch.nn.functional.cosine_similarity(pooled16, pooled, dim=1).numpy().astype(np.float32),
+                        hf_bf16_logit_diff=(logits16 - logits).abs().amax(1).numpy().astype(np.float32),
+                        weights_seed=1, wave_seed=1234, head_seed=3)
 
 
 def make_long60(out_dir):

@@ -260,18 +260,21 @@ def test_extract_cli_writes_reference_format_and_head_argmax_matches(tmp_path, c
     assert float((torch.from_numpy(dm["embedding"])[0] - torch.from_numpy(d["embedding"]).max(0).values).abs().max()) < 1e-5
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("impl", [2, 0, 1], ids=["tcgen05_two_pipelines", "tcgen05_one_item", "mma_sync"])
 def test_attention_kernels_against_oracle(debug_encoder, weights, impl):
-    """Both attention kernels (tcgen05/TMEM product path and the mma.sync cross-check) on a ragged batch whose lengths
-    hit: a single frame, < 1 key block, exactly 128 / 129 frames, > 160 (table clamps), several key blocks."""
-    lengths = [400, 6400, 41200, 41520, 64000, 100000, 250000]     # T = 1, 19, 128, 129, 199, 312, 781
+    """The attention kernels (the two-pipeline tcgen05/TMEM product kernel, its one-item-per-SM predecessor and the mma.sync
+    cross-check) on a ragged batch whose lengths hit: a single frame, < 1 key block, 33 / 64 / 65 frames (tile and key-half
+    edges), exactly 128 / 129 frames, > 160 (table clamps), > 193 (second table round), several key blocks."""
+    lengths = [400, 6400, 10640, 20560, 20880, 41200, 41520, 64000, 100000, 250000]     # T = 1, 19, 33, 64, 65, 128, 129, 199, 312, 781
     waves = H.make_waves(lengths, seed=17)
     debug_encoder.debug_set("stop_after_layer", 0)
-    debug_encoder.debug_set("attn_impl", impl)
+    debug_encoder.debug_set("attn_impl", 1 if impl == 1 else 0)
+    debug_encoder.debug_set("attn_p2", 1 if impl == 2 else 0)
+    debug_encoder.debug_set("attn_p2_max_frames", 1 << 30)          # every utterance through the kernel under test
     try:
         taps = H.oracle_taps(weights, waves, n_layers=1)
         pooled, hidden, info = H.run_encoder(debug_encoder, waves)
-        assert info["frames"].tolist() == [1, 19, 128, 129, 199, 312, 781]
+        assert info["frames"].tolist() == [1, 19, 33, 64, 65, 128, 129, 199, 312, 781]
         ctx = debug_encoder.debug_buffer("ctx").float().cpu()
         for u, t in enumerate(taps):
             r0 = int(info["rows"][u])
@@ -281,7 +284,9 @@ def test_attention_kernels_against_oracle(debug_encoder, weights, impl):
             assert H.rel_err(got, ref) < STAGE_REL_MAX, (impl, u, H.rel_err(got, ref))
     finally:
         debug_encoder.debug_set("stop_after_layer", -1)
-        debug_encoder.debug_set("attn_impl", -1)
+        debug_encoder.debug_set("attn_impl", 0)
+        debug_encoder.debug_set("attn_p2", 1)
+        debug_encoder.debug_set("attn_p2_max_frames", 224)
 
 
 def test_pipelined_host_path_equals_device_path(encoder):
@@ -300,10 +305,16 @@ def test_pipelined_host_path_equals_device_path(encoder):
 def test_config5_subset_against_hf_golden_with_intent_head(encoder):
     """SURVEY.md 8(d) "Config 5": a fixed 512-utterance subset of the 70k SLURP-shaped set (the bench's own lengths,
     weights seed 1, waveforms seed 1234) against tests/golden/config5_hf.npz -- the unmodified HF module's pooled
-    embeddings (stored fp16) and IntentClassifier(average) logits with the seed-3 Linear(768,101), made by
-    oracle/make_golden.py --config5-only.  Bars: pooled cosine >= 0.999 and max rel err < 3e-2 for every utterance;
-    the intent argmax equals the reference's wherever the reference's own top-2 margin exceeds 0.03 (bf16 operands move
-    a logit by up to 1.6e-2: measured 10 of 512 differ, all with reference margins < 8.4e-3), and on >= 97 % of all 512.  The fused head's logits are the ones compared."""
+    embeddings (fp32) and IntentClassifier(average) logits with the seed-3 Linear(768,101), made by
+    oracle/make_golden.py --config5-only.  The fused head's logits are the ones compared.
+
+    The yardstick for "bf16 compute" is in the same file: the SAME HF module run under torch.autocast(bfloat16) -- the
+    reference's own arithmetic at this path's operand precision -- moves the pooled embedding by up to 1.12e-2 (max rel err;
+    mean 8.1e-3; min cosine 0.999958), a logit by up to 1.8e-2, and flips the intent argmax on 12 of the 512 utterances, all
+    near-ties (fp32 top-2 margin < 8.4e-3).  north_star's "argmax identical" is therefore not attainable at bf16 by the
+    reference itself; the bars here are: cosine >= 0.999; max rel err within 1.25x of what HF-in-bf16 shows; every argmax
+    difference is a near-tie by the same measure (fp32 margin below twice the largest logit movement), never more of them
+    than HF-in-bf16 produces plus a quarter, and the argmax is identical wherever the fp32 margin exceeds 0.02."""
     from loco_asr_b200.encoder import LocoSpeechT5Encoder
     from loco_asr_b200.head import IntentHead
     from loco_asr_b200.synth import synth_state_dict
@@ -322,17 +333,23 @@ def test_config5_subset_against_hf_golden_with_intent_head(encoder):
         p, hp, lg = enc.encode_packed(wave, [len(x) for x in waves], with_head=True)
         pooled[sel] = p.cpu()
         logits[sel] = lg.cpu()
-    ref = torch.from_numpy(g["pooled_f16"].astype(np.float32))
+    ref = torch.from_numpy(g["pooled"])
     cos = torch.nn.functional.cosine_similarity(pooled, ref, dim=1)
     rel = (pooled - ref).abs().amax(dim=1) / ref.abs().amax(dim=1)
     agree = logits.argmax(dim=1).numpy() == g["argmax"]
-    print(f"config 5: min cosine {float(cos.min()):.6f}, max rel err {float(rel.max()):.5f}, argmax agreement {agree.mean():.4f} "
-          f"({int((~agree).sum())} of {len(ids)} differ; largest reference margin among them "
-          f"{float(g['margin'][~agree].max()) if (~agree).any() else 0.0:.5f}), max |logit diff| "
-          f"{float((logits - torch.from_numpy(g['logits'])).abs().max()):.5f}")
-    assert float(cos.min()) >= COS_MIN and float(rel.max()) < POOLED_REL_MAX
-    assert agree[g["margin"] > 0.03].all()
-    assert agree.mean() >= 0.97
+    logit_diff = float((logits - torch.from_numpy(g["logits"])).abs().max())
+    hf_flips = int((g["hf_bf16_argmax"] != g["argmax"]).sum())
+    hf_rel, hf_logit = float(g["hf_bf16_rel_err"].max()), float(g["hf_bf16_logit_diff"].max())
+    print(f"config 5: min cosine {float(cos.min()):.6f} (HF in bf16: {float(g['hf_bf16_cosine'].min()):.6f}), max rel err "
+          f"{float(rel.max()):.5f} (HF in bf16: {hf_rel:.5f}), mean rel err {float(rel.mean()):.5f} (HF in bf16: {float(g['hf_bf16_rel_err'].mean()):.5f}), "
+          f"argmax differs on {int((~agree).sum())} of {len(ids)} (HF in bf16: {hf_flips}; largest fp32 margin among ours "
+          f"{float(g['margin'][~agree].max()) if (~agree).any() else 0.0:.5f}), max |logit diff| {logit_diff:.5f} (HF in bf16: {hf_logit:.5f})")
+    assert float(cos.min()) >= COS_MIN
+    assert float(rel.max()) <= 1.25 * hf_rel and float(rel.mean()) <= 1.1 * float(g["hf_bf16_rel_err"].mean())
+    assert logit_diff <= 1.25 * hf_logit
+    assert agree[g["margin"] > 0.02].all()
+    assert int((~agree).sum()) <= hf_flips + hf_flips // 4
+    assert not (~agree).any() or float(g["margin"][~agree].max()) < 2 * logit_diff
 
 
 @pytest.mark.parametrize("max_frames", [131072, 196608])

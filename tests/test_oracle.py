@@ -95,16 +95,16 @@ def test_intent_head_argmax_is_stable_under_bf16_noise(sd):
 
 def test_restatement_matches_config5_golden_subset():
     """Two of the 512 config-5 utterances (the shortest ones, to stay within seconds): the functional restatement with the
-    seed-1 weights against the HF pooled embeddings in tests/golden/config5_hf.npz (stored fp16: 5e-4 relative rounding)."""
+    seed-1 weights against the HF pooled embeddings in tests/golden/config5_hf.npz (fp32)."""
     g = np.load(os.path.join(GOLD, "config5_hf.npz"))
     sd = synth_state_dict(seed=1)
     for i in np.argsort(g["n_samples"], kind="stable")[:2]:
         x = torch.from_numpy(synth_wave(int(g["n_samples"][i]), 1234, int(g["ids"][i])))
         got = O.encode_utterance(sd, x).mean(0)
-        ref = torch.from_numpy(g["pooled_f16"][i].astype(np.float32))
-        assert float((got - ref).abs().max() / ref.abs().max()) < 2e-3
+        ref = torch.from_numpy(g["pooled"][i])
+        assert float((got - ref).abs().max() / ref.abs().max()) < 5e-5
         logit = torch.nn.functional.linear(got, *synth_head(3))
-        assert float((logit - torch.from_numpy(g["logits"][i])).abs().max()) < 1e-3
+        assert float((logit - torch.from_numpy(g["logits"][i])).abs().max()) < 1e-4
 
 
 def test_restatement_matches_hf_on_a_60s_segment():
