@@ -88,7 +88,7 @@ def build(verbose: bool = False) -> str:
 def load(debug: bool = False):
     """dlopen the library and attach signatures.  Raises LocoError if it has not been built.  ``debug=True`` loads the
     LOCO_DEBUG build (cross-check kernels + the knobs that select them), which only the tests and tools/ use."""
-    path = DEBUG_LIB_PATH if debug else LIB_PATH
+    path = os.environ.get("LOCO_ASR_LIB") or (DEBUG_LIB_PATH if debug else LIB_PATH)     # the override serves both
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

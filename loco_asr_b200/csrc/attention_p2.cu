@@ -65,7 +65,10 @@ constexpr int TM_S = 192, TM_P = 96, TM_O = 0, TM_L = 64, TM_PIPE = 256, P2_TMEM
 constexpr int G_ROUND1 = 256;           // table columns of the first G round; the rest (<= 64) reuses columns [0, 64)
 constexpr int G_LO_CHUNKS = 2;          // 32-column chunks that must be drained before the second round may be issued
 constexpr int G_EARLY_S = 192;          // tables up to this many columns leave S's columns alone
-constexpr float kLazyRescale = 8.0f;    // log2 units
+#ifndef LOCO_LAZY_RESCALE
+#define LOCO_LAZY_RESCALE 8.0f          // tools/parity_toggles.py builds a variant with 0 (rescale at every new maximum)
+#endif
+constexpr float kLazyRescale = LOCO_LAZY_RESCALE;    // log2 units
 
 struct __align__(8) PBars {             // one set per pipeline
     uint64_t q_full[2], q_empty[2], kv_full[NS], kv_empty[NS];

@@ -80,7 +80,10 @@ constexpr int FA_THREADS = (FA_SOFTMAX_WARPS + 4) * 32;     // 12 warps: the reg
 constexpr int TM_S = 0, TM_P = 128, TM_O = 192, TM_G = 320, FA_TMEM_COLS = 512;   // S 2x64, P 2x32, O 2x64, G 192
 constexpr int G_ROUND1 = 192;           // G columns of the first MMA round (6 chunks); the rest reuses the first 128 columns
 constexpr int G_LO_CHUNKS = 4;          // chunks that must be drained before the second round may be issued
-constexpr float kLazyRescale = 8.0f;    // log2 units
+#ifndef LOCO_LAZY_RESCALE
+#define LOCO_LAZY_RESCALE 8.0f          // tools/parity_toggles.py builds a variant with 0 (rescale at every new maximum)
+#endif
+constexpr float kLazyRescale = LOCO_LAZY_RESCALE;    // log2 units
 
 struct __align__(8) FaBars {
     uint64_t pe_full, g_full, g_lo_free, g2_full, ga_empty, o_full;

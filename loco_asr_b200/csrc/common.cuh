@@ -37,9 +37,13 @@ constexpr float kLnEps = 1e-5f;
 // erf -- the GELU epilogues (conv layers, FFN1) are issue-bound, not MMA-bound, so this is what sets their speed.
 // Max |error| vs exact: 2.6e-5 absolute, two orders below the bf16 rounding of the stored activation.
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef LOCO_EX2_PRECISE        // tools/parity_toggles.py: what the MUFU approximation costs in parity (nothing measurable)
+    return exp2f(x);
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 __device__ __forceinline__ float gelu_erf(float v) {
     const float v2 = fminf(v * v, 64.0f);
@@ -74,6 +78,9 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
 #define LOCO_GELU_TANH 1
 #endif
 __device__ __forceinline__ float2 gelu_erf2(float2 v) {
+#ifdef LOCO_GELU_ERF           // tools/parity_toggles.py: the library erff instead of the fitted forms
+    return make_float2(0.5f * v.x * (1.0f + erff(v.x * 0.70710678118654752f)), 0.5f * v.y * (1.0f + erff(v.y * 0.70710678118654752f)));
+#endif
     float2 v2 = mul_f32x2(v, v);
     v2.x = fminf(v2.x, 64.0f);
     v2.y = fminf(v2.y, 64.0f);
