@@ -52,15 +52,35 @@ constexpr int SM_Q = SM_PE + kRelCols * 128;             // 2 slots
 constexpr int SM_KV = SM_Q + 2 * Q_TILE_B;               // [2 pipelines][NS entries]
 constexpr int SM_QT = SM_KV + 2 * NS * ENTRY_B;          // [2 pipelines][64 rows][QT_LD] fp16
 constexpr int SM_ONES = SM_QT + 2 * PQ * QT_LD * 2;      // [16][64] bf16 ones: B operand of the row-sum MMA (2 KB)
-constexpr int SM_XH = SM_ONES + 16 * 128;                // [2 parities][2 pipelines][2 halves][64 rows] block maxima
-constexpr int SM_DESC = SM_XH + 8 * PQ * 4;              // [2 pipelines][4] int4 item descriptors
+#ifndef LOCO_P2_NH
+#define LOCO_P2_NH 2
+#endif
+#ifndef LOCO_P2_SKEW
+#define LOCO_P2_SKEW 0
+#endif
+constexpr int NH = LOCO_P2_NH;          // threads per query row: each takes FK / NH keys of every block, in NH warps of the same
+                                        // TMEM lane quadrant.  NH = 4 (sixteen softmax warps at 96 registers, 16 scores per thread and
+                                        // block) was built and measured: the gather, exponential and drain phases take the SAME number
+                                        // of cycles as with NH = 2 (phase trace, profiles/r03_attention_p2_experiments.md) -- an item's
+                                        // rows live in two TMEM lane quadrants = two SM sub-partitions whatever the warp count, and
+                                        // each phase is bound by those two sub-partitions' MUFU / the SM's LSU, not by per-warp latency
+#ifndef LOCO_P2_POLY_MASK
+#define LOCO_P2_POLY_MASK 0xA           // every other pair of exponentials on the FMA pipe (common.cuh ex2_poly2): -5 % at 128-192 frames
+#endif
+constexpr int KW = FK / NH;             // keys per thread and block
+constexpr int OW = kHeadDim / NH;       // accumulator columns per thread (rescale, epilogue)
+static_assert(NH == 2 || NH == 4, "attention_p2: threads per row");
+constexpr int SM_XH = SM_ONES + 16 * 128;                // [2 parities][2 pipelines][NH parts][64 rows] block maxima
+constexpr int SM_DESC = SM_XH + 2 * 2 * NH * PQ * 4;     // [2 pipelines][4] int4 item descriptors
 constexpr int SM_BARS = SM_DESC + 2 * 4 * 16;
 constexpr int P2_SMEM = SM_BARS + 512 + 1024;
 static_assert(P2_SMEM <= 232448, "attention_p2: shared memory budget");
-constexpr int P2_SOFTMAX_WARPS = 8;
-constexpr int WARP_LOAD = 8;            // warps 8, 9: loaders of pipeline 0 / 1
-constexpr int WARP_MMA = 10;            // warps 10, 11: MMA issuers of pipeline 0 / 1
-constexpr int P2_THREADS = 12 * 32;
+constexpr int P2_SOFTMAX_WARPS = 4 * NH;
+constexpr int WARP_LOAD = P2_SOFTMAX_WARPS;         // two loader warps: pipeline 0 / 1
+constexpr int WARP_MMA = P2_SOFTMAX_WARPS + 2;      // two MMA issuer warps: pipeline 0 / 1
+constexpr int P2_THREADS = (P2_SOFTMAX_WARPS + 4) * 32;
+constexpr int PIPE_THREADS = 2 * NH * 32;           // softmax threads of one pipeline
+constexpr int ROW_THREADS = NH * 32;                // softmax threads of one lane quadrant (the NH warps that share 32 rows)
 constexpr int TM_S = 192, TM_P = 96, TM_O = 0, TM_L = 64, TM_PIPE = 256, P2_TMEM_COLS = 512;
 constexpr int G_ROUND1 = 256;           // table columns of the first G round; the rest (<= 64) reuses columns [0, 64)
 constexpr int G_LO_CHUNKS = 2;          // 32-column chunks that must be drained before the second round may be issued
@@ -165,22 +185,22 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             PBars& b = bars->p[p];
             for (int s = 0; s < 2; ++s) {
                 mbar_init(smem_u32(&b.q_full[s]), 1);
-                mbar_init(smem_u32(&b.q_empty[s]), 1 + 4);           // the MMA warp + the pipeline's four softmax warps
+                mbar_init(smem_u32(&b.q_empty[s]), 1 + 2 * NH);      // the MMA warp + the pipeline's softmax warps
             }
             for (int s = 0; s < NS; ++s) {
                 mbar_init(smem_u32(&b.kv_full[s]), 1);
                 mbar_init(smem_u32(&b.kv_empty[s]), 1);
             }
             mbar_init(smem_u32(&b.g_full), 1);
-            mbar_init(smem_u32(&b.g_lo_free), 128);
+            mbar_init(smem_u32(&b.g_lo_free), PIPE_THREADS);
             mbar_init(smem_u32(&b.g2_full), 1);
-            mbar_init(smem_u32(&b.tab_done), 128);
+            mbar_init(smem_u32(&b.tab_done), PIPE_THREADS);
             mbar_init(smem_u32(&b.s_full), 1);
-            mbar_init(smem_u32(&b.s_empty), 128);
-            mbar_init(smem_u32(&b.p_full), 128);
+            mbar_init(smem_u32(&b.s_empty), PIPE_THREADS);
+            mbar_init(smem_u32(&b.p_full), PIPE_THREADS);
             mbar_init(smem_u32(&b.pv_done), 1);
             mbar_init(smem_u32(&b.o_full), 1);
-            mbar_init(smem_u32(&b.o_empty), 128);
+            mbar_init(smem_u32(&b.o_empty), PIPE_THREADS);
         }
         mbar_fence_init();
         fence_proxy_async_smem();
@@ -333,7 +353,7 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
     } else {
         // ===================== softmax warps =====================
         const int q = warp & 3;                    // TMEM lane quadrant
-        const int h = warp >> 2;                   // key half inside a 64-key block
+        const int h = warp >> 2;                   // which KW keys of a 64-key block (and which share of the drain / epilogue)
         const int p = q >> 1;                      // pipeline
         PBars& B = bars->p[p];
         const int rloc = (q & 1) * 32 + lane;      // row inside the item
@@ -346,11 +366,20 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         uint32_t cnt = 0, n_g2 = 0;                // key blocks seen, items with a second G round
 
         int n = 0;
+#if LOCO_P2_SKEW > 0
+        // Start pipeline 1 a fraction of an item late.  Both pipelines walk items of the same length (the batch is sorted), so
+        // started together they stay in lock-step and meet in every phase -- both gather (LDS), both exponentiate (MUFU) -- and a
+        // collision slows both equally, so it never dissolves.  Offset once, they stay offset for the same reason.
+        if (p == 1) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < LOCO_P2_SKEW) { }
+        }
+#endif
         for (int item = 2 * (int)blockIdx.x + p; item < n_items; item += stride, ++n) {
-            if (q == 0) TR(h, n, 0);
+            if (q == 0 && h < 2) TR(h, n, 0);
             bar_wait(smem_u32(&B.g_full), (uint32_t)(n & 1), 310);      // also: the item's descriptor is in place
             tc_fence_after();
-            if (q == 0) TR(h, n, 1);
+            if (q == 0 && h < 2) TR(h, n, 1);
             Item it;
             it.set(descs[p * 4 + (n & 3)]);
             const bool active = (q & 1) * 32 < it.nr;
@@ -380,7 +409,7 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             {   // round 1, one chunk at a time (keeping the next chunk's TMEM load in flight measured 7 % slower: registers)
                 const int hi1 = min(c_last, G_ROUND1 / 32 - 1);
                 if (active)
-                    for (int c = h; c < G_LO_CHUNKS; c += 2)
+                    for (int c = h; c < G_LO_CHUNKS; c += NH)
                         if (c >= c_first && c <= hi1) {
                             uint32_t v[32];
                             tmem_ld_32x32(t_lane + c * 32, v);
@@ -392,7 +421,7 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     mbar_arrive(smem_u32(&B.g_lo_free));
                 }
                 if (active)
-                    for (int c = G_LO_CHUNKS + h; c <= hi1; c += 2)
+                    for (int c = G_LO_CHUNKS + ((h - G_LO_CHUNKS) & (NH - 1)); c <= hi1; c += NH)      // chunk c belongs to part c % NH
                         if (c >= c_first) {
                             uint32_t v[32];
                             tmem_ld_32x32(t_lane + c * 32, v);
@@ -405,7 +434,7 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 ++n_g2;
                 tc_fence_after();
                 if (active)
-                    for (int c = G_ROUND1 / 32 + h; c <= c_last; c += 2) {
+                    for (int c = G_ROUND1 / 32 + h; c <= c_last; c += NH) {
                         if (c < c_first) continue;
                         uint32_t v[32];
                         tmem_ld_32x32(t_lane + (c - G_ROUND1 / 32) * 32, v);
@@ -415,25 +444,26 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&B.tab_done));                   // G has left TMEM
-            if (q == 0) TR(h, n, 2);
-            if (active) named_bar_sync(pair_id, 64);              // both column sets of my rows are in the table
+            if (q == 0 && h < 2) TR(h, n, 2);
+            if (active) named_bar_sync(pair_id, ROW_THREADS);     // all column sets of my rows are in the table
 
             float row_max = -INFINITY;
             const int ic = min(i, it.T - 1);                      // clamped row for table indexing on the slow path
             const int col0 = i + kMaxRel - it.cbase;              // table column of key 0
             for (int j = 0; j < it.n_kv; ++j, ++cnt) {
                 const int jlen = it.klen(j);
-                const bool mine = active && h * 32 < jlen;        // this key half of the block holds keys
-                const int jc = j * FK + h * 32, mylen = jlen - h * 32;
-                if (q == 0 && j == 0) TR(h, n, 3);
+                const bool mine = active && h * KW < jlen;        // this part of the block holds keys
+                const int jc = j * FK + h * KW, mylen = jlen - h * KW;
+                if (q == 0 && h < 2 && j == 0) TR(h, n, 3);
                 bar_wait(smem_u32(&B.s_full), cnt & 1, 312);
                 tc_fence_after();
-                if (q == 0 && j == 0) TR(h, n, 4);
-                uint32_t su[32];                   // scores, fp32 bit patterns (one array from the TMEM load to the exponentials)
-                if (mine) tmem_ld_32x32(t_s + h * 32, su);
+                if (q == 0 && h < 2 && j == 0) TR(h, n, 4);
+                uint32_t su[KW];                   // scores, fp32 bit patterns (one array from the TMEM load to the exponentials)
+                if (mine) tmem_ld_cols<KW>(t_s + h * KW, su);
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) asm volatile("" : "+r"(su[e]));
+                for (int e = 0; e < KW; ++e) asm volatile("" : "+r"(su[e]));
+                if (q == 0 && h < 2 && j == 0) TR(h, n, 13);
                 tc_fence_before();
                 mbar_arrive(smem_u32(&B.s_empty));                // the next S may be written
 #define SC(e) __uint_as_float(su[e])
@@ -441,29 +471,29 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 float cbias = 0.f;                 // scalar bias of a fully clamped half block, folded into the exp argument
                 float mloc = -INFINITY;
                 if (mine) {
-                    const int rel_max = iw0 + 31 - jc, rel_min = iw0 - (jc + 31);
+                    const int rel_max = iw0 + 31 - jc, rel_min = iw0 - (jc + KW - 1);
                     if (rel_max < kMaxRel && rel_min >= -kMaxRel) {
                         const unsigned short* base = reinterpret_cast<const unsigned short*>(my_qt) + (col0 - jc);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) SET_SC(e, add_f32_f16(SC(e), base[-e]));
+                        for (int e = 0; e < KW; ++e) SET_SC(e, add_f32_f16(SC(e), base[-e]));
                     } else if (rel_min >= kMaxRel - 1 || rel_max <= -kMaxRel) {
                         cbias = __half2float(my_qt[(rel_min >= kMaxRel - 1 ? kRelCols - 1 : 0) - it.cbase]);
                     } else {
                         const unsigned short* base = reinterpret_cast<const unsigned short*>(my_qt) + (kMaxRel - it.cbase);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
+                        for (int e = 0; e < KW; ++e) {
                             const int rel = max(-kMaxRel, min(kMaxRel - 1, ic - (jc + e)));
                             SET_SC(e, add_f32_f16(SC(e), base[rel]));
                         }
                     }
-                    if (mylen < 32) {
+                    if (mylen < KW) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e)
+                        for (int e = 0; e < KW; ++e)
                             if (e >= mylen) SET_SC(e, -INFINITY);
                     }
                     float cm[4] = {SC(0), SC(1), SC(2), SC(3)};      // four chains for ILP
 #pragma unroll
-                    for (int e = 4; e < 32; e += 4) {
+                    for (int e = 4; e < KW; e += 4) {
                         cm[0] = fmaxf(cm[0], SC(e + 0));
                         cm[1] = fmaxf(cm[1], SC(e + 1));
                         cm[2] = fmaxf(cm[2], SC(e + 2));
@@ -471,95 +501,104 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     }
                     mloc = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) + cbias;
                 }
-                // the two threads of a row agree on the block maximum (double-buffered by block parity: the partner reads my
+                // the NH threads of a row agree on the block maximum (double-buffered by block parity: the partners read my
                 // value right after the barrier and I next write this buffer two barriers later)
                 if (active) {
-                    float* xhb = xh + ((cnt & 1) * 2 + p) * 2 * PQ;
+                    float* xhb = xh + ((cnt & 1) * 2 + p) * NH * PQ;
                     xhb[h * PQ + rloc] = mloc;
-                    if (q == 0 && j == 0) TR(h, n, 5);
-                    named_bar_sync(pair_id, 64);
-                    mloc = fmaxf(mloc, xhb[(h ^ 1) * PQ + rloc]);
+                    if (q == 0 && h < 2 && j == 0) TR(h, n, 5);
+                    named_bar_sync(pair_id, ROW_THREADS);
+#pragma unroll
+                    for (int o = 1; o < NH; ++o) mloc = fmaxf(mloc, xhb[((h + o) & (NH - 1)) * PQ + rloc]);
                 }
-                if (q == 0 && j == 0) TR(h, n, 6);
+                if (q == 0 && h < 2 && j == 0) TR(h, n, 6);
                 if (j > 0) {            // P and O are free once the previous P.V has completed (issued a block ago)
                     bar_wait(smem_u32(&B.pv_done), (cnt - 1) & 1, 314);
                     tc_fence_after();
                 }
                 // (only rows that exist vote: the lanes past the utterance's last query hold a neighbour's rows, and letting them
-                //  trigger a rescale would make the valid rows' rounding depend on the batch the utterance travelled in.  Both
+                //  trigger a rescale would make the valid rows' rounding depend on the batch the utterance travelled in.  All
                 //  warps of a row see the same maxima, so they take the same decision and keep identical running maxima.)
                 if (active && __any_sync(0xffffffffu, rloc < it.nr && mloc > row_max + kLazyRescale)) {
                     const float mx = fmaxf(row_max, mloc);
                     const float corr = ex2_approx(row_max - mx);      // first block: exp2(-inf) = 0
                     row_max = mx;
-                    if (j > 0) {        // each of the two warps rescales its half of the accumulator's columns; the first also the row sum
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_o + h * 32, v);
+                    if (j > 0) {        // each of the row's warps rescales its share of the accumulator's columns; the first also the row sum
+                        uint32_t v[OW];
+                        tmem_ld_cols<OW>(t_o + h * OW, v);
                         uint32_t lsum = 0;
                         if (h == 0) lsum = tmem_ld_32x1(t_l);
-                        tmem_ld_wait(v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < OW; ++e) asm volatile("" : "+r"(v[e]));
                         asm volatile("" : "+r"(lsum));
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * corr);
-                        tmem_st_32x32(t_o + h * 32, v);
+                        for (int e = 0; e < OW; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * corr);
+                        tmem_st_cols<OW>(t_o + h * OW, v);
                         if (h == 0) tmem_st_32x1(t_l, __float_as_uint(__uint_as_float(lsum) * corr));
                     }
                 }
-                // ---- P = exp2(S - max) as packed bf16 pairs: my half's 16 columns of the P buffer ---------------------------
+                // ---- P = exp2(S - max) as packed bf16 pairs: my part's KW / 2 columns of the P buffer -----------------------
                 if (mine) {
                     const float sub = cbias - row_max;
                     const float2 sub2 = make_float2(sub, sub);
-                    uint32_t pp[16];
+                    uint32_t pp[KW / 2];
 #pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
+                    for (int e = 0; e < KW; e += 2) {
                         const float2 d = add_f32x2(make_float2(SC(e), SC(e + 1)), sub2);
-                        pp[e >> 1] = pack_bf16(ex2_approx(d.x), ex2_approx(d.y));
+                        const float2 pr = ex2_pair<LOCO_P2_POLY_MASK>(d, e >> 1);
+                        pp[e >> 1] = pack_bf16(pr.x, pr.y);
                     }
-                    tmem_st_32x16(t_p + h * 16, pp);
+                    if (q == 0 && h < 2 && j == 0) TR(h, n, 14);
+                    tmem_st_cols<KW / 2>(t_p + h * (KW / 2), pp);
                 }
                 tmem_st_wait();
+                if (q == 0 && h < 2 && j == 0) TR(h, n, 15);
                 tc_fence_before();
                 mbar_arrive(smem_u32(&B.p_full));
-                if (q == 0 && j == 0) TR(h, n, 7);
+                if (q == 0 && h < 2 && j == 0) TR(h, n, 7);
 #undef SC
 #undef SET_SC
             }
             // ---- epilogue: O / l as bf16, staged in the item's own Q rows (its MMAs are done once o_full has completed; the
             // loader refills the slot only after this epilogue has arrived on q_empty) and written with full 128-byte lines
             const uint32_t stage = sbase + SM_Q + (n & 1) * Q_TILE_B + p * (PQ * 128);
-            if (q == 0) TR(h, n, 8);
+            if (q == 0 && h < 2) TR(h, n, 8);
             bar_wait(smem_u32(&B.o_full), (uint32_t)(n & 1), 309);
             tc_fence_after();
-            if (q == 0) TR(h, n, 9);
+            if (q == 0 && h < 2) TR(h, n, 9);
             if (active) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_o + h * 32, v);
+                uint32_t v[OW];
+                tmem_ld_cols<OW>(t_o + h * OW, v);
                 uint32_t lsum = tmem_ld_32x1(t_l);            // l = P . 1, accumulated by the tensor core beside O
-                tmem_ld_wait(v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < OW; ++e) asm volatile("" : "+r"(v[e]));
                 asm volatile("" : "+r"(lsum));
                 const float inv = 1.0f / __uint_as_float(lsum);
 #pragma unroll
-                for (int e = 0; e < 32; e += 8) {
+                for (int e = 0; e < OW; e += 8) {
                     uint4 o4;
                     o4.x = pack_bf16(__uint_as_float(v[e + 0]) * inv, __uint_as_float(v[e + 1]) * inv);
                     o4.y = pack_bf16(__uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv);
                     o4.z = pack_bf16(__uint_as_float(v[e + 4]) * inv, __uint_as_float(v[e + 5]) * inv);
                     o4.w = pack_bf16(__uint_as_float(v[e + 6]) * inv, __uint_as_float(v[e + 7]) * inv);
-                    const int chunk = h * 4 + (e >> 3);                 // 16-byte chunk of the row's 128-byte line
+                    const int chunk = h * (OW / 8) + (e >> 3);          // 16-byte chunk of the row's 128-byte line
                     sts128(stage + rloc * 128 + ((chunk ^ (rloc & 7)) << 4), o4);
                 }
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&B.o_empty));                    // O has left TMEM: the next item's G may be issued
-            if (q == 0) TR(h, n, 10);
-            named_bar_sync(pipe_id, 128);                         // all rows of the item are staged
-            if (q == 0) TR(h, n, 11);
+            if (q == 0 && h < 2) TR(h, n, 10);
+            named_bar_sync(pipe_id, PIPE_THREADS);                // all rows of the item are staged
+            if (q == 0 && h < 2) TR(h, n, 11);
             {
                 bf16* out = ctx + (int64_t)it.row0 * kHidden + it.head * kHeadDim;
-                const int w4 = (q & 1) * 2 + h;                   // which of the pipeline's four warps: rows 16 w4 + [0, 16)
+                constexpr int RW = PQ / (2 * NH);                 // rows per warp: 8 lanes per row, 4 full lines per instruction
+                const int w4 = (q & 1) * NH + h;                  // which of the pipeline's softmax warps: rows RW w4 + [0, RW)
 #pragma unroll
-                for (int r4 = 0; r4 < 4; ++r4) {
-                    const int r = w4 * 16 + r4 * 4 + (lane >> 3), chunk = lane & 7;
+                for (int r4 = 0; r4 < RW / 4; ++r4) {
+                    const int r = w4 * RW + r4 * 4 + (lane >> 3), chunk = lane & 7;
                     if (r < it.nr) {
                         const uint4 o4 = lds128(stage + r * 128 + ((chunk ^ (r & 7)) << 4));
                         *reinterpret_cast<uint4*>(out + (int64_t)r * kHidden + chunk * 8) = o4;
@@ -569,7 +608,7 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             fence_proxy_async_smem();             // generic accesses to the slot are ordered before the TMA refill
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&B.q_empty[n & 1]));
-            if (q == 0) TR(h, n, 12);
+            if (q == 0 && h < 2) TR(h, n, 12);
         }
     }
     tc_fence_before();
@@ -604,13 +643,13 @@ int launch_attention_p2(const void* qkv_map, const void* pe_map, const PcTile* t
         const unsigned origin = t[0][6][0];
         fprintf(stderr, "attention_p2 phase trace of CTA 0 pipeline 0, items 6..9 (items %d, grid %d); SM clocks since softmax warp 0 entered item 6\n"
                         "softmax: 0 top, 1 g_full, 2 drained (tab_done), 3 at s_full wait, 4 s_full, 5 bias+max done, 6 maxima exchanged, 7 P stored (block 0), "
-                        "8 key loop done, 9 o_full, 10 O staged, 11 all staged, 12 stored\n"
+                        "8 key loop done, 9 o_full, 10 O staged, 11 all staged, 12 stored, 13 S in registers (block 0), 14 exponentials done (block 0), 15 P in TMEM (block 0)\n"
                         "mma: 0 top, 1 q_full, 2 o_empty, 3 G issued, 4 tab_done, 5 S0 issued, 6 p_full(0), 7 item done\n", n_items, grid);
         const char* names[3] = {"softmax h0", "softmax h1", "mma"};
         for (int r = 0; r < 3; ++r)
             for (int n = 6; n < 10; ++n) {
                 fprintf(stderr, "%-10s item %d:", names[r], n);
-                for (int k = 0; k < (r == 2 ? 8 : 13); ++k) fprintf(stderr, " %6d", (int)(t[r][n][k] - origin));
+                for (int k = 0; k < (r == 2 ? 8 : 16); ++k) fprintf(stderr, " %6d", (int)(t[r][n][k] - origin));
                 fprintf(stderr, "\n");
             }
     }

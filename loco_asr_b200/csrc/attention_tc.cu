@@ -77,6 +77,8 @@ constexpr int FA_SOFTMAX_WARPS = 8;
 constexpr int WARP_LOAD = FA_SOFTMAX_WARPS;                 // warps 8, 9: TMA loaders of group 0 / 1
 constexpr int WARP_MMA = FA_SOFTMAX_WARPS + 2;              // warps 10, 11: MMA issuers of group 0 / 1
 constexpr int FA_THREADS = (FA_SOFTMAX_WARPS + 4) * 32;     // 12 warps: the register file is allocated in 4-warp steps anyway
+constexpr int FA_AUX_REGS = 104;         // setmaxnreg: the loader / MMA warpgroup (warps 8-11) releases 168 - 104 registers per thread,
+constexpr int FA_SOFTMAX_REGS = 200;    // the two softmax warpgroups take 32 each: no spills (168 for everybody left 92 B of them in the key loop)
 constexpr int TM_S = 0, TM_P = 128, TM_O = 192, TM_G = 320, FA_TMEM_COLS = 512;   // S 2x64, P 2x32, O 2x64, G 192
 constexpr int G_ROUND1 = 192;           // G columns of the first MMA round (6 chunks); the rest reuses the first 128 columns
 constexpr int G_LO_CHUNKS = 4;          // chunks that must be drained before the second round may be issued
@@ -84,6 +86,9 @@ constexpr int G_LO_CHUNKS = 4;          // chunks that must be drained before th
 #define LOCO_LAZY_RESCALE 8.0f          // tools/parity_toggles.py builds a variant with 0 (rescale at every new maximum)
 #endif
 constexpr float kLazyRescale = LOCO_LAZY_RESCALE;    // log2 units
+#ifndef LOCO_TC_POLY_MASK
+#define LOCO_TC_POLY_MASK 0x8           // one pair of exponentials in four on the FMA pipe (common.cuh ex2_poly2): -2 % at 256 and 2999 frames;
+#endif                                  // every other pair (0xA) measured no faster, three in four slower: FFMA2 costs the FMA pipe as much as two FFMAs
 
 struct __align__(8) FaBars {
     uint64_t pe_full, g_full, g_lo_free, g2_full, ga_empty, o_full;
@@ -208,6 +213,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
     pdl_wait();          // the prologue above overlapped the previous kernel's tail; nothing before this line touches global data
 
     if (warp == WARP_LOAD || warp == WARP_LOAD + 1) {
+        setmaxnreg_dec<FA_AUX_REGS>();
         // ===================== loaders: one per group (group 0's also brings pe_k and the Q tiles) =====================
         const int g = warp - WARP_LOAD;
         if (lane == 0) {
@@ -256,6 +262,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
             }
         }
     } else if (warp == WARP_MMA || warp == WARP_MMA + 1) {
+        setmaxnreg_dec<FA_AUX_REGS>();
         // ===================== MMA issuers: one per group =====================
         // Group g's warp issues S_j and P_j.V_j for its blocks j = g, g+2, ...; group 0's also issues G.  The whole warp runs
         // the (uniform) control flow so descriptors live in uniform registers; one elected lane issues the tcgen05
@@ -432,6 +439,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
         }
     } else {
         // ===================== softmax warps =====================
+        setmaxnreg_inc<FA_SOFTMAX_REGS>();
         const int q = warp & 3;                    // TMEM lane quadrant
         const int g = warp >> 2;                   // group: key blocks j = g, g + 2, ...
         const int row = q * 32 + lane;
@@ -679,7 +687,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
 #pragma unroll
                     for (int e = 0; e < 32; e += 2) {
                         const float2 d = add_f32x2(make_float2(SC(c, e), SC(c, e + 1)), sub2);
-                        const float2 p = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+                        const float2 p = ex2_pair<LOCO_TC_POLY_MASK>(d, e >> 1);
                         ps[(e >> 1) & 1] = add_f32x2(ps[(e >> 1) & 1], p);
                         pp[e >> 1] = pack_bf16(p.x, p.y);
                     }

@@ -69,6 +69,31 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2*>(&rd);
 }
+// exp2 of a pair on the FMA pipe instead of the MUFU: x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5 * 2^23,
+// 2^f on [-1/2, 1/2] as a cubic (relative error 7.5e-5, fifty times below the bf16 rounding of the probabilities it feeds), and n
+// added into the exponent field.  Inputs are clamped at -125 (result ~2e-38 for masked / far-away keys); inputs above 127 are not
+// expected (the softmax subtracts a maximum that is at most 2^8 stale).  The attention kernels send a fixed subset of the key
+// columns of every block through this path: their exponential phase is bound by the 4 MUFU results per clock of the two SM
+// sub-partitions an item's rows live on, while those sub-partitions' FMA pipes idle.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -125.0f);
+    x.y = fmaxf(x.y, -125.0f);
+    const float2 magic = make_float2(12582912.0f, 12582912.0f);
+    const float2 t = add_f32x2(x, magic);
+    const float2 n = add_f32x2(t, make_float2(-12582912.0f, -12582912.0f));
+    const float2 f = fma_f32x2(n, make_float2(-1.0f, -1.0f), x);
+    float2 p = fma_f32x2(f, make_float2(0.055171459913253784f, 0.055171459913253784f), make_float2(0.2426108568906784f, 0.2426108568906784f));
+    p = fma_f32x2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+    p = fma_f32x2(p, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+    return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                       __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+// MASK bit (i & 3) set: pair i of a thread's key columns takes the FMA-pipe path (0xA = every other pair, 0x8 = one in four, 0 = none).
+template <int MASK>
+__device__ __forceinline__ float2 ex2_pair(float2 x, int pair) {       // `pair` is a compile-time constant at every call site
+    if ((MASK >> (pair & 3)) & 1) return ex2_poly2(x);
+    return make_float2(ex2_approx(x.x), ex2_approx(x.y));
+}
 // gelu_erf on a pair with the packed FP32 pipe (FMUL2 / FFMA2 / FADD2).
 // LOCO_GELU_TANH (default): the same odd quintic u(v), evaluated as 0.5 v (1 + tanh(u)) with ONE MUFU op per element
 // (tanh.approx.f32, |abs err| < 5e-4 on tanh -> < 2.5e-4 |v| on the result, below the bf16 rounding of the stored
@@ -111,6 +136,13 @@ __device__ __forceinline__ float add_f32_f16(float a, unsigned short h) {
     asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(r) : "h"(h), "f"(a));
     return r;
 }
+// Register reallocation between warpgroups (4 consecutive warps): the loader / MMA-issuer warpgroup gives registers back, the
+// softmax warpgroups take them.  The kernel launches with the __launch_bounds__ allocation (65536 / threads); the pool is what
+// the dec side released.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -345,6 +377,32 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// N consecutive 32-bit columns of this warp's 32 lanes, N = 8 / 16 / 32 (one row per thread)
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]) {
+    static_assert(N == 8 || N == 16 || N == 32, "tmem_ld_cols");
+    if constexpr (N == 32) tmem_ld_32x32(taddr, r);
+    else if constexpr (N == 16) tmem_ld_32x16(taddr, r);
+    else tmem_ld_32x8(taddr, r);
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)[N]) {
+    static_assert(N == 8 || N == 16 || N == 32, "tmem_st_cols");
+    if constexpr (N == 32) tmem_st_32x32(taddr, r);
+    else if constexpr (N == 16) tmem_st_32x16(taddr, r);
+    else tmem_st_32x8(taddr, r);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Wait for the outstanding tcgen05.ld's, then pin `r` behind the wait: the empty volatile asm statements give the

@@ -115,3 +115,25 @@ def test_gelu_sigmoid_quintic_error_bound():
     worst = np.abs(g2 - ref) + 2.0 ** -10.987 * 0.5 * np.abs(v)
     keep = np.abs(v) <= 8
     assert (worst[keep] / np.maximum(np.abs(v[keep]), 1e-3)).max() < 2.0 ** -9          # half a bf16 ulp of |v|
+
+
+def test_exp2_polynomial_error_bound():
+    """numpy emulation (fp32, bit-level) of csrc/common.cuh ex2_poly2 -- round-to-nearest split through the 1.5 * 2^23 magic
+    number, cubic on [-1/2, 1/2], integer add into the exponent field -- against 2^x over the range the softmax feeds it:
+    (-inf, 8].  Relative error below 1e-4, i.e. 40x under the bf16 rounding (2^-9) of the probability it produces."""
+    x = np.concatenate([np.linspace(-125, 8, 1_000_001), [-126.0, -1e4, -np.inf, 0.0, -0.5, 0.5, -0.49999, 7.99999]]).astype(np.float32)
+    xc = np.maximum(x, np.float32(-125))
+    magic = np.float32(12582912.0)
+    t = (xc + magic).astype(np.float32)
+    n = (t - magic).astype(np.float32)
+    f = (xc - n).astype(np.float32)
+    assert np.abs(f).max() <= 0.5
+    p = np.float32(0.055171459913253784) * f + np.float32(0.2426108568906784)
+    p = (p.astype(np.float32) * f + np.float32(0.6932609677314758)).astype(np.float32)
+    p = (p * f + np.float32(0.9999281167984009)).astype(np.float32)
+    bits = p.view(np.int32).astype(np.int64) + ((t.view(np.int32).astype(np.int64) << 23) & 0xFFFFFFFF)
+    got = (bits & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+    ref = np.exp2(xc.astype(np.float64))
+    assert np.isfinite(got).all() and (got > 0).all()
+    assert (np.abs(got.astype(np.float64) / ref - 1)).max() < 1e-4
+    assert got[np.isneginf(x)][0] < 1e-37                     # masked keys: 2^-125, nothing against a row sum >= 1

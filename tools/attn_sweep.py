@@ -8,7 +8,7 @@ from loco_asr_b200.encoder import LocoSpeechT5Encoder
 from loco_asr_b200.synth import synth_state_dict
 
 enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device="cuda:0", debug=True)
-KERNELS = [("p2", 0, 1), ("tc", 0, 0), ("mma.sync", 1, 0)]
+KERNELS = [k for k in [("p2", 0, 1), ("tc", 0, 0), ("mma.sync", 1, 0)] if k[0] in os.environ.get("ATTN_SWEEP_KERNELS", "p2,tc,mma.sync").split(",")]
 for T in [int(x) for x in (sys.argv[1:] or [50, 100, 149, 200, 256, 320, 499, 768, 1024, 1499, 2999])]:
     n_samples = (T - 1) * 320 + 400
     n = max(1, 64000 // (T + 2))
