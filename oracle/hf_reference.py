@@ -62,6 +62,51 @@ def hf_encode_unpadded(model, waves: Sequence[np.ndarray]) -> List[torch.Tensor]
 
 
 @torch.no_grad()
+def hf_stage_taps(model, wave: np.ndarray) -> Dict[str, torch.Tensor]:
+    """Stage-by-stage intermediates of the UNMODIFIED HF module for one unpadded utterance, taken with forward hooks (nothing of
+    the restatement is involved): the tap names and time-major [T_i, C] layouts of oracle/speecht5_oracle.py.  ``l0_qkv`` is
+    [q * 64^-1/2 | k | v] (HF scales q right after q_proj, modeling_speecht5.py:905)."""
+    taps: Dict[str, torch.Tensor] = {}
+    hooks = []
+
+    def out_hook(name, fn=lambda o: o):
+        def h(_m, _i, o):
+            taps[name] = fn(o[0] if isinstance(o, tuple) else o).detach().clone()
+        return h
+
+    def in_hook(name):
+        def h(_m, i):
+            taps[name] = i[0][0].detach().clone()
+        return h
+
+    pre, enc = model.prenet, model.wrapped_encoder
+    for i in (0, 1, 6):
+        hooks.append(pre.feature_encoder.conv_layers[i].register_forward_hook(out_hook(f"conv{i}", lambda o: o[0].t())))
+    hooks.append(pre.feature_projection.layer_norm.register_forward_hook(out_hook("proj_ln", lambda o: o[0])))
+    hooks.append(pre.feature_projection.projection.register_forward_hook(out_hook("proj", lambda o: o[0])))
+    hooks.append(pre.pos_conv_embed.register_forward_hook(out_hook("pos_conv", lambda o: o[0])))
+    hooks.append(pre.register_forward_hook(out_hook("prenet_out", lambda o: o[0])))
+    hooks.append(enc.layer_norm.register_forward_hook(out_hook("enc_in", lambda o: o[0])))
+    l0 = enc.layers[0]
+    for nm in ("q_proj", "k_proj", "v_proj"):
+        hooks.append(getattr(l0.attention, nm).register_forward_hook(out_hook("_" + nm, lambda o: o[0])))
+    hooks.append(l0.attention.out_proj.register_forward_pre_hook(in_hook("l0_ctx")))
+    hooks.append(l0.layer_norm.register_forward_hook(out_hook("l0_ln1", lambda o: o[0])))
+    hooks.append(l0.feed_forward.output_dense.register_forward_pre_hook(in_hook("l0_mid")))
+    for l in (0, 5, 11):
+        hooks.append(enc.layers[l].register_forward_hook(out_hook(f"layer{l}", lambda o: o[0])))
+    try:
+        last = model(input_values=torch.as_tensor(wave, dtype=torch.float32)[None]).last_hidden_state[0]
+    finally:
+        for h in hooks:
+            h.remove()
+    head_dim = model.config.hidden_size // model.config.encoder_attention_heads
+    taps["l0_qkv"] = torch.cat([taps.pop("_q_proj") * head_dim ** -0.5, taps.pop("_k_proj"), taps.pop("_v_proj")], dim=1)
+    taps["last_hidden"] = last
+    return taps
+
+
+@torch.no_grad()
 def hf_encode_padded_batches(model, waves: Sequence[np.ndarray], batch_size: int = 2):
     """The reference's literal loop: ``batch_size = 2``, ``padding="longest"``, zero padding value and an
     int attention mask (extract_speecht5_base_embeddings_slurp.py:60,67,108;
