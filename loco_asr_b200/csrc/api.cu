@@ -117,7 +117,8 @@ struct loco_handle {
     int ln_impl = 0;            // 0 = LayerNorms of the transformer layers deferred into the GEMM epilogues [default], 1 = LayerNorm kernels
     int attn_impl = 0;          // 0 = tcgen05 [default, the only product kernel], 1 = mma.sync cross-check, -1 = by length (round-1 routing)
     bool attn_p2 = true;        // utterances shorter than attn_p2_max_frames go to the two-pipeline tcgen05 kernel (attention_p2.cu),
-    int attn_p2_max_frames = 224;   // the others to the one-item-per-SM tcgen05 kernel (attention_tc.cu)
+    int attn_p2_max_frames = 193;   // the others to the one-item-per-SM tcgen05 kernel (attention_tc.cu),
+    bool attn_p2_tail = true;       // except a tail of at most 64 query rows, which becomes one two-pipeline item
     int attn_tc_min_frames = 193;   // utterances with at least this many frames use the tcgen05 attention kernel,
     int attn_tc_lo = 76, attn_tc_hi = 128;   // ... and so do utterances that fill most of one 128-query tile (see loco_encode)
     alignas(64) CUtensorMap pe_map;   // pe_k [320, 64] for the tcgen05 attention kernel
@@ -837,7 +838,7 @@ static int finalize_impl(loco_handle* h) {
 namespace {
 
 uint64_t knob_state(const loco_handle* h) {
-    return ((uint64_t)(h->attn_p2 ? 1 : 0) << 60) ^ ((uint64_t)(uint32_t)h->attn_p2_max_frames << 20) ^ ((uint64_t)(uint32_t)(h->attn_impl + 1) << 48) ^ ((uint64_t)(uint32_t)h->attn_tc_min_frames << 32) ^
+    return ((uint64_t)(h->attn_p2 ? 1 : 0) << 60) ^ ((uint64_t)(h->attn_p2_tail ? 1 : 0) << 61) ^ ((uint64_t)(uint32_t)h->attn_p2_max_frames << 20) ^ ((uint64_t)(uint32_t)(h->attn_impl + 1) << 48) ^ ((uint64_t)(uint32_t)h->attn_tc_min_frames << 32) ^
            ((uint64_t)(uint32_t)h->attn_tc_lo << 16) ^ (uint64_t)(uint32_t)h->attn_tc_hi;
 }
 
@@ -887,10 +888,19 @@ int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loc
             // Which tcgen05 kernel: by the utterance's OWN frame count (never by its batch-mates, so its result does not depend
             // on the batch it travels in).  tools/attn_sweep.py, ms per layer at 64k frames, two-pipeline / one-item: 64 frames
             // 0.15 / 0.38, 128: 0.21 / 0.26, 149: 0.32 / 0.56, 192: 0.29 / 0.50, 256: 0.36 / 0.33, 499: 0.57 / 0.49, 2999: 2.1 / 1.6.
-            if (h->attn_p2 && t6 < h->attn_p2_max_frames)
+            // r03g (finer sweep, both kernels after setmaxnreg / the cubic exp2): the cost is a sawtooth in the frame count -- the
+            // one-item kernel pays a whole 128-query tile for a tail of a few rows (128 -> 132 frames: 0.21 -> 0.47 ms), the
+            // two-pipeline kernel a 64-query item (0.20 -> 0.33).  So: up to 192 frames everything goes to the two-pipeline kernel;
+            // above, full 128-query tiles and tails of more than 64 rows go to the one-item kernel and a tail of at most 64 rows
+            // becomes one two-pipeline item (264 frames: 0.44-0.49 either kernel alone).  Which kernel computes a query row depends
+            // only on (frame count, row index).
+            if (h->attn_p2 && t6 < h->attn_p2_max_frames) {
                 for (int f = 0; f < t6; f += 64) p->at_tiles64.push_back({L.meta[u].row6 + f, f, t6, 0});
-            else
-                for (int f = 0; f < t6; f += 128) p->at_tiles.push_back({L.meta[u].row6 + f, f, t6, 0});
+            } else {
+                int f = 0;
+                for (; t6 - f > (h->attn_p2 && h->attn_p2_tail ? 64 : 0); f += 128) p->at_tiles.push_back({L.meta[u].row6 + f, f, t6, 0});
+                if (f < t6) p->at_tiles64.push_back({L.meta[u].row6 + f, f, t6, 0});
+            }
         } else {
             p->at_utts.push_back(u);
             if (t6 > p->at_ms_max_t6) p->at_ms_max_t6 = t6;
@@ -1393,6 +1403,7 @@ int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
     else if (!strcmp(name, "attn_impl")) h->attn_impl = (int)value;
     else if (!strcmp(name, "attn_p2")) h->attn_p2 = value != 0;
     else if (!strcmp(name, "attn_p2_max_frames")) h->attn_p2_max_frames = (int)value;
+    else if (!strcmp(name, "attn_p2_tail")) h->attn_p2_tail = value != 0;
     else if (!strcmp(name, "attn_tc_min_frames")) h->attn_tc_min_frames = (int)value;
     else if (!strcmp(name, "attn_tc_lo")) h->attn_tc_lo = (int)value;
     else if (!strcmp(name, "attn_tc_hi")) h->attn_tc_hi = (int)value;

@@ -154,7 +154,7 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity, int tag)
 // Phase timeline of CTA 0, pipeline 0 (first 64 items), compiled in with -DLOCO_ATTN_TRACE: SM clock at fixed points of softmax
 // warp 0 (role 0), softmax warp 4 (role 1: the other key half) and the MMA warp (role 2); printed when LOCO_ATTN_TRACE is set.
 #ifdef LOCO_ATTN_TRACE
-__device__ unsigned g_p2_trace[3][64][16];
+__device__ unsigned g_p2_trace[3][64][24];
 #define TR(role, item_n, k)                                                                          \
     do {                                                                                             \
         if (blockIdx.x == 0 && lane == 0 && (item_n) < 64) {                                         \
@@ -335,14 +335,17 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 bar_wait(smem_u32(&B.p_full), n_blk & 1, 209);
                 tc_fence_after();
                 if (p == 0 && j == 0) TR(2, n, 6);
+                if (p == 0 && j == it.n_kv - 1) TR(2, n, 8);
                 const uint64_t dv = umma_desc_sw128_mnmajor(ring + slot * ENTRY_B + KV_TILE_B);
                 const int ks = (it.klen(j) + 15) >> 4;
                 if (elect_one()) {
                     for (int k = 0; k < ks; ++k) umma_bf16_ts(d_o, d_p + k * 8, dv + (uint64_t)(k * 128), kIdescPV, (j | k) != 0 ? 1u : 0u);
                     for (int k = 0; k < ks; ++k) umma_bf16_ts(d_l, d_p + k * 8, d_ones + (uint64_t)(k * 2), kIdescL, (j | k) != 0 ? 1u : 0u);   // l += P . 1
+                    if (p == 0 && j == it.n_kv - 1) TR(2, n, 9);
                     umma_commit(smem_u32(&B.pv_done));
                     umma_commit(smem_u32(&B.kv_empty[slot]));
                 }
+                if (p == 0 && j == it.n_kv - 1) TR(2, n, 10);
             }
             if (elect_one()) {
                 umma_commit(smem_u32(&B.o_full));
@@ -458,12 +461,14 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 bar_wait(smem_u32(&B.s_full), cnt & 1, 312);
                 tc_fence_after();
                 if (q == 0 && h < 2 && j == 0) TR(h, n, 4);
+                if (q == 0 && h < 2 && j == it.n_kv - 1) TR(h, n, 16);
                 uint32_t su[KW];                   // scores, fp32 bit patterns (one array from the TMEM load to the exponentials)
                 if (mine) tmem_ld_cols<KW>(t_s + h * KW, su);
                 tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < KW; ++e) asm volatile("" : "+r"(su[e]));
                 if (q == 0 && h < 2 && j == 0) TR(h, n, 13);
+                if (q == 0 && h < 2 && j == it.n_kv - 1) TR(h, n, 17);
                 tc_fence_before();
                 mbar_arrive(smem_u32(&B.s_empty));                // the next S may be written
 #define SC(e) __uint_as_float(su[e])
@@ -507,15 +512,18 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                     float* xhb = xh + ((cnt & 1) * 2 + p) * NH * PQ;
                     xhb[h * PQ + rloc] = mloc;
                     if (q == 0 && h < 2 && j == 0) TR(h, n, 5);
+                    if (q == 0 && h < 2 && j == it.n_kv - 1) TR(h, n, 18);
                     named_bar_sync(pair_id, ROW_THREADS);
 #pragma unroll
                     for (int o = 1; o < NH; ++o) mloc = fmaxf(mloc, xhb[((h + o) & (NH - 1)) * PQ + rloc]);
                 }
                 if (q == 0 && h < 2 && j == 0) TR(h, n, 6);
+                if (q == 0 && h < 2 && j == it.n_kv - 1) TR(h, n, 19);
                 if (j > 0) {            // P and O are free once the previous P.V has completed (issued a block ago)
                     bar_wait(smem_u32(&B.pv_done), (cnt - 1) & 1, 314);
                     tc_fence_after();
                 }
+                if (q == 0 && h < 2 && j == it.n_kv - 1) TR(h, n, 20);
                 // (only rows that exist vote: the lanes past the utterance's last query hold a neighbour's rows, and letting them
                 //  trigger a rescale would make the valid rows' rounding depend on the batch the utterance travelled in.  All
                 //  warps of a row see the same maxima, so they take the same decision and keep identical running maxima.)
@@ -554,6 +562,7 @@ attention_p2_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_co
                 }
                 tmem_st_wait();
                 if (q == 0 && h < 2 && j == 0) TR(h, n, 15);
+                if (q == 0 && h < 2 && j == it.n_kv - 1) TR(h, n, 21);
                 tc_fence_before();
                 mbar_arrive(smem_u32(&B.p_full));
                 if (q == 0 && h < 2 && j == 0) TR(h, n, 7);
@@ -637,19 +646,20 @@ int launch_attention_p2(const void* qkv_map, const void* pe_map, const PcTile* t
 #ifdef LOCO_ATTN_TRACE
     static int traced = 0;
     if (!rc && getenv("LOCO_ATTN_TRACE") != nullptr && traced++ == 2) {
-        static unsigned t[3][64][16];
+        static unsigned t[3][64][24];
         rc = (int)cudaStreamSynchronize(s);
         if (!rc) rc = (int)cudaMemcpyFromSymbol(t, g_p2_trace, sizeof t);
         const unsigned origin = t[0][6][0];
         fprintf(stderr, "attention_p2 phase trace of CTA 0 pipeline 0, items 6..9 (items %d, grid %d); SM clocks since softmax warp 0 entered item 6\n"
                         "softmax: 0 top, 1 g_full, 2 drained (tab_done), 3 at s_full wait, 4 s_full, 5 bias+max done, 6 maxima exchanged, 7 P stored (block 0), "
                         "8 key loop done, 9 o_full, 10 O staged, 11 all staged, 12 stored, 13 S in registers (block 0), 14 exponentials done (block 0), 15 P in TMEM (block 0)\n"
-                        "mma: 0 top, 1 q_full, 2 o_empty, 3 G issued, 4 tab_done, 5 S0 issued, 6 p_full(0), 7 item done\n", n_items, grid);
+                        "          last block: 16 s_full, 17 S in registers, 18 bias + max done, 19 maxima exchanged, 20 pv_done, 21 P in TMEM\n"
+                        "mma: 0 top, 1 q_full, 2 o_empty, 3 G issued, 4 tab_done, 5 S0 issued, 6 p_full(0), 7 item done, last block: 8 p_full, 9 P.V issued, 10 committed\n", n_items, grid);
         const char* names[3] = {"softmax h0", "softmax h1", "mma"};
         for (int r = 0; r < 3; ++r)
             for (int n = 6; n < 10; ++n) {
                 fprintf(stderr, "%-10s item %d:", names[r], n);
-                for (int k = 0; k < (r == 2 ? 8 : 16); ++k) fprintf(stderr, " %6d", (int)(t[r][n][k] - origin));
+                for (int k = 0; k < (r == 2 ? 11 : 22); ++k) fprintf(stderr, " %6d", (int)(t[r][n][k] - origin));
                 fprintf(stderr, "\n");
             }
     }

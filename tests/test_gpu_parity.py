@@ -260,17 +260,18 @@ def test_extract_cli_writes_reference_format_and_head_argmax_matches(tmp_path, c
     assert float((torch.from_numpy(dm["embedding"])[0] - torch.from_numpy(d["embedding"]).max(0).values).abs().max()) < 1e-5
 
 
-@pytest.mark.parametrize("impl", [2, 0, 1], ids=["tcgen05_two_pipelines", "tcgen05_one_item", "mma_sync"])
+@pytest.mark.parametrize("impl", [3, 2, 0, 1], ids=["product_mix", "tcgen05_two_pipelines", "tcgen05_one_item", "mma_sync"])
 def test_attention_kernels_against_oracle(debug_encoder, weights, impl):
-    """The attention kernels (the two-pipeline tcgen05/TMEM product kernel, its one-item-per-SM predecessor and the mma.sync
-    cross-check) on a ragged batch whose lengths hit: a single frame, < 1 key block, 33 / 64 / 65 frames (tile and key-half
+    """The attention kernels (the product's per-tile mix of the two tcgen05/TMEM kernels -- 199 frames: two one-item tiles, 312 and
+    781: one-item tiles plus a two-pipeline tail item --, each of the two alone, and the mma.sync cross-check) on a ragged batch
+    whose lengths hit: a single frame, < 1 key block, 33 / 64 / 65 frames (tile and key-half
     edges), exactly 128 / 129 frames, > 160 (table clamps), > 193 (second table round), several key blocks."""
     lengths = [400, 6400, 10640, 20560, 20880, 41200, 41520, 64000, 100000, 250000]     # T = 1, 19, 33, 64, 65, 128, 129, 199, 312, 781
     waves = H.make_waves(lengths, seed=17)
     debug_encoder.debug_set("stop_after_layer", 0)
     debug_encoder.debug_set("attn_impl", 1 if impl == 1 else 0)
-    debug_encoder.debug_set("attn_p2", 1 if impl == 2 else 0)
-    debug_encoder.debug_set("attn_p2_max_frames", 1 << 30)          # every utterance through the kernel under test
+    debug_encoder.debug_set("attn_p2", 1 if impl >= 2 else 0)
+    debug_encoder.debug_set("attn_p2_max_frames", 193 if impl == 3 else 1 << 30)      # 1 << 30: every utterance through the kernel under test
     try:
         taps = H.oracle_taps(weights, waves, n_layers=1)
         pooled, hidden, info = H.run_encoder(debug_encoder, waves)
@@ -286,7 +287,7 @@ def test_attention_kernels_against_oracle(debug_encoder, weights, impl):
         debug_encoder.debug_set("stop_after_layer", -1)
         debug_encoder.debug_set("attn_impl", 0)
         debug_encoder.debug_set("attn_p2", 1)
-        debug_encoder.debug_set("attn_p2_max_frames", 224)
+        debug_encoder.debug_set("attn_p2_max_frames", 193)
 
 
 def test_pipelined_host_path_equals_device_path(encoder):
