@@ -885,9 +885,7 @@ int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loc
         tc = h->attn_impl == 0 || (h->attn_impl < 0 && (t6 >= h->attn_tc_min_frames || (t6 >= h->attn_tc_lo && t6 <= h->attn_tc_hi)));
 #endif
         if (tc) {
-            // Which tcgen05 kernel: by the utterance's OWN frame count (never by its batch-mates, so its result does not depend
-            // on the batch it travels in).  tools/attn_sweep.py, ms per layer at 64k frames, two-pipeline / one-item: 64 frames
-            // 0.15 / 0.38, 128: 0.21 / 0.26, 149: 0.32 / 0.56, 192: 0.29 / 0.50, 256: 0.36 / 0.33, 499: 0.57 / 0.49, 2999: 2.1 / 1.6.
+            // Which tcgen05 kernel takes which query tile.
             // r03g (finer sweep, both kernels after setmaxnreg / the cubic exp2): the cost is a sawtooth in the frame count -- the
             // one-item kernel pays a whole 128-query tile for a tail of a few rows (128 -> 132 frames: 0.21 -> 0.47 ms), the
             // two-pipeline kernel a 64-query item (0.20 -> 0.33).  So: up to 192 frames everything goes to the two-pipeline kernel;

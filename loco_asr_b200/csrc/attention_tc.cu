@@ -39,10 +39,12 @@
 // pv_done.  Every softmax thread runs the same barrier skeleton whether or not its rows exist, and no waiter can be lapped
 // by two phases of its barrier (see ga_empty / o_full).  Set LOCO_ATTN_DEBUG=1 to have a stuck wait reported per role.
 //
-// Measured (tools/attn_sweep.py, 64k frames per batch, per layer): 0.24 ms at T = 128, 0.31 ms at 256, 0.47 ms at 499, 0.94 ms
-// at 1499, 1.60 ms at 2999 (380 TFLOP/s of Q K^T + P V + table FLOPs) -- 1.3-2x the mma.sync kernel; where a 128-query tile is mostly
-// empty (< 76 or 129..192 frames) the per-item fixed costs (drain, epilogue, ~10 barrier hand-offs) dominate and the
-// mma.sync kernel (attention.cu) takes the utterance (chosen per utterance in loco_encode).
+// Measured (tools/attn_sweep.py, 64k frames per batch, per layer; profiles/r03b_attn_sweep.txt): 0.21 ms at T = 128, 0.29 ms at 256,
+// 0.41 ms at 499, 0.84 ms at 1499, 1.49 ms at 2999 (411 TFLOP/s of Q K^T + P V + table FLOPs).  An item costs ~3.6 us + 0.95 us per
+// key block whether its tile holds 128 rows or 4, so a tile that is at most half full goes to the two-pipeline kernel
+// (attention_p2.cu) instead -- chosen per query tile from (frame count, row index) in api.cu.
+// One pair of exponentials in four is evaluated on the FMA pipe (common.cuh ex2_poly2); setmaxnreg moves 64 registers per
+// thread from the loader / MMA warpgroup to the softmax warpgroups (200 each: the key loop no longer spills).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
