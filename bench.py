@@ -45,7 +45,7 @@ def parse_args():
     p.add_argument("--utts", type=int, default=70000)
     p.add_argument("--max-frames", type=int, default=131072)
     p.add_argument("--e2e-steps", type=int, default=16)
-    p.add_argument("--cpu-sample", type=int, default=96, help="utterances in the bounded CPU-baseline sample")
+    p.add_argument("--cpu-sample", type=int, default=384, help="utterances in the bounded CPU-baseline sample (~15 s of CPU work on 16 cores)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--seed", type=int, default=1234)
     p.add_argument("--no-stage-events", action="store_true", help="debug: time the steps without the per-launch CUDA events (no roofline)")
