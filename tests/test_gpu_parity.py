@@ -184,6 +184,26 @@ def test_submodule_state_dict_shims_and_weight_norm_spellings(weights):
         enc2.finalize()
 
 
+def test_fairseq_checkpoint_names_load_to_the_same_encoder(encoder, weights):
+    """A fairseq SpeechT5 ``ckpt["model"]`` (synthesised by renaming the seeded weights backwards, plus tensors the encoder never
+    reads) goes through loco_asr_b200.fairseq_keys.fairseq_to_hf -- the table form of map_speecht5_hf.py:34-168 -- into the two
+    load_state_dict shims and gives the bits the HF-named weights give."""
+    from loco_asr_b200.encoder import LocoSpeechT5Encoder
+    from loco_asr_b200.fairseq_keys import fairseq_to_hf, hf_to_fairseq_name
+    model = {hf_to_fairseq_name(k): v for k, v in weights.items()}
+    assert None not in model
+    model["decoder.layers.0.fc1.weight"] = torch.zeros(4, 4)
+    model["encoder.proj.weight"] = torch.zeros(81, 768)
+    enc_sd, speech_sd, _ = fairseq_to_hf(model)
+    enc = LocoSpeechT5Encoder(device="cuda:0")
+    enc.wrapped_encoder.load_state_dict(enc_sd)
+    enc.prenet.load_state_dict(speech_sd)
+    waves = H.make_waves([24000, 9000, 70000], seed=31)
+    got, _, _ = H.run_encoder(enc, waves)
+    want, _, _ = H.run_encoder(encoder, waves)
+    assert torch.equal(got, want)
+
+
 def test_host_buffer_path_equals_device_path(encoder):
     waves = H.make_waves([16000, 52000, 23000, 9000], seed=12)
     lengths = [len(w) for w in waves]
