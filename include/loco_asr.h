@@ -197,11 +197,11 @@ LOCO_API int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_
 
 /* ---- debug / test hooks (not part of the product surface) -------------------------------------------
  * The product library (libloco_asr.so) contains only the product kernels; loco_debug_set fails on it.  The cross-check
- * kernels (SIMT GEMM, single-CTA tcgen05 GEMM, mma.sync positional conv and attention, stand-alone LayerNorm path) and the
+ * kernels (SIMT GEMM, single-CTA tcgen05 GEMM, mma.sync and one-phase tcgen05 positional conv, mma.sync attention, stand-alone LayerNorm path) and the
  * knobs that select them are compiled only with -DLOCO_DEBUG into libloco_asr_debug.so, which the unit tests load. */
 LOCO_API int loco_is_debug_build(void);
-/* name: "gemm_impl" (2 = tcgen05 CTA pair, cta_group::2 [default], 0 = tcgen05 single CTA, 1 = SIMT reference), "posconv_impl" (0 = tcgen05 [default],
- * 1 = mma.sync cross-check), "ln_impl" (0 = the transformer layers' LayerNorms deferred into the GEMM epilogues [default, needs gemm_impl 2],
+/* name: "gemm_impl" (2 = tcgen05 CTA pair, cta_group::2 [default], 0 = tcgen05 single CTA, 1 = SIMT reference), "posconv_impl" (0 = polyphase tcgen05 [default],
+ * 1 = mma.sync cross-check, 2 = one-phase tcgen05 cross-check), "ln_impl" (0 = the transformer layers' LayerNorms deferred into the GEMM epilogues [default, needs gemm_impl 2],
  * 1 = LayerNorm kernels), "attn_impl" (-1 = per utterance by its own frame count [default], 0 = tcgen05, 1 = mma.sync), "attn_tc_min_frames" / "attn_tc_lo" / "attn_tc_hi" (the frame ranges that select the tcgen05 kernel), "stop_after_layer"
  * (-1 = run all).  */
 LOCO_API int loco_debug_set(loco_handle* h, const char* name, int64_t value);

@@ -52,6 +52,8 @@ struct Layout {
     int max_t0 = 0, max_t6 = 0, max_slot6 = 0, chunks = 1;
     std::vector<UttMeta> meta;
     std::vector<PcTile> pc_tiles;
+    std::vector<int32_t> pp_map;                // positional conv: timeline frame -> row (internal.h, posconv_pp.cu)
+    int n_vtiles = 0;
     size_t off_stats1 = 0, off_stats2 = 0;      // deferred LayerNorm: row statistics of attn_res / ffn_res, [R6, 6, 2] fp32
     size_t off_partial = 0, off_scale = 0, off_shift = 0, off_rowframe = 0;
     std::map<std::string, Buf> bufs;
@@ -73,7 +75,8 @@ struct loco_batch_plan {
     std::vector<PcTile> at_tiles64;             // two-pipeline tcgen05 kernel: 64-query tiles of the utterances routed to it
     std::vector<int32_t> at_utts;               // LOCO_DEBUG builds: utterances routed to the mma.sync cross-check kernel
     int at_ms_max_t6 = 0;
-    uint8_t* dev = nullptr;                     // [meta | pc_tiles | at_tiles | at_utts]
+    uint8_t* dev = nullptr;                     // [meta | pc_tiles | at_tiles | at_utts | pp_map]
+    size_t d_ppmap = 0;
     size_t d_meta = 0, d_pctiles = 0, d_attiles = 0, d_attiles64 = 0, d_atutts = 0, dev_bytes = 0;
     int device = 0;
     bool cached = false;                        // owned by the handle's plan cache (loco_encode), not by the caller
@@ -94,7 +97,8 @@ struct loco_handle {
     float *pln_w = nullptr, *pln_b = nullptr, *proj_b = nullptr;
     bf16* proj_w = nullptr;
     bf16* pos_w = nullptr;      // [g][tap][out][in]          (mma.sync debug kernel)
-    bf16* pos_w_tc = nullptr;   // [g][tap][in/8][out][in%8]  (tcgen05 kernel: per-tap UMMA B operand)
+    bf16* pos_w_tc = nullptr;   // [g][tap][in/8][out][in%8]  (one-phase tcgen05 debug kernel: per-tap UMMA B operand)
+    bf16* pos_w_pp = nullptr;   // [g][in/8][3 zero taps | tap | 8 zero taps][out][in%8]  (polyphase tcgen05 kernel)
     float* pos_b = nullptr;
     float* sin_table = nullptr;
     int sin_rows = 0;
@@ -389,6 +393,18 @@ int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L)
         if (slot > L->max_slot6) L->max_slot6 = slot;
     }
     if ((row << 6) > (int64_t)INT32_MAX / 2) return fail(h, LOCO_ERR_INVALID, "batch too large: more than 2^30 conv0 frames");
+    {
+        // positional conv timeline: utterances back to back with kPosPPHalo zero frames between neighbours
+        const int64_t total = out_row + (int64_t)n_utts * kPosPPHalo;
+        L->n_vtiles = (int)((total + kPosPPTile - 1) / kPosPPTile);
+        L->pp_map.assign((size_t)L->n_vtiles * kPosPPTile + 2 * kPosPPHalo, -1);
+        size_t pos = kPosPPHalo;
+        for (int u = 0; u < n_utts; ++u) {
+            const UttMeta& m = L->meta[u];
+            for (int f = 0; f < m.t6; ++f) L->pp_map[pos + f] = m.row6 + f;
+            pos += (size_t)m.t6 + kPosPPHalo;
+        }
+    }
     L->R6 = row;
     L->total_frames = out_row;
     L->total_samples = off;
@@ -595,9 +611,10 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
     if (!rc) rc = gemm_tc2_init();
     if (!rc) rc = attention_tc_init();
     if (!rc) rc = attention_p2_init();
-    if (!rc) rc = posconv_tc_init();
+    if (!rc) rc = posconv_pp_init();
     if (!rc) rc = frontend_init();
 #ifdef LOCO_DEBUG
+    if (!rc) rc = posconv_tc_init();
     if (!rc) rc = gemm_tc_init();
     if (!rc) rc = attention_init();
     if (!rc) rc = posconv_init();
@@ -710,6 +727,7 @@ static int finalize_impl(loco_handle* h) {
         for (double& x : norm) x = sqrt(x);
         std::vector<bf16> w((size_t)16 * 128 * 48 * 48);     // [group][tap][out_local][in]
         std::vector<bf16> wt((size_t)16 * 128 * 48 * 48);    // [group][tap][in / 8][out_local][in % 8]
+        std::vector<bf16> wp((size_t)16 * 6 * kPosPPTaps * 48 * 8, to_bf16_host(0.f));    // [group][in / 8][3 + tap][out_local][in % 8]
         for (int o = 0; o < 768; ++o)
             for (int c = 0; c < 48; ++c)
                 for (int j = 0; j < 128; ++j) {
@@ -717,11 +735,13 @@ static int finalize_impl(loco_handle* h) {
                     const size_t gj = (size_t)(o / 48) * 128 + j;
                     w[(gj * 48 + (o % 48)) * 48 + c] = to_bf16_host(val);
                     wt[((gj * 6 + c / 8) * 48 + (o % 48)) * 8 + (c % 8)] = to_bf16_host(val);
+                    wp[((((size_t)(o / 48) * 6 + c / 8) * kPosPPTaps + 3 + j) * 48 + (o % 48)) * 8 + (c % 8)] = to_bf16_host(val);
                 }
 #ifdef LOCO_DEBUG
         if ((rc = upload(h, w, &h->pos_w))) return rc;
-#endif
         if ((rc = upload(h, wt, &h->pos_w_tc))) return rc;
+#endif
+        if ((rc = upload(h, wp, &h->pos_w_pp))) return rc;
         if ((rc = upload_f32(h, "prenet.pos_conv_embed.conv.bias", {768}, &h->pos_b))) return rc;
     }
     }  // has_speech
@@ -932,6 +952,7 @@ int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loc
     p->d_attiles = place(p->at_tiles.size() * sizeof(PcTile));
     p->d_attiles64 = place(p->at_tiles64.size() * sizeof(PcTile));
     p->d_atutts = place(p->at_utts.size() * sizeof(int32_t));
+    p->d_ppmap = place(L.pp_map.size() * sizeof(int32_t));
     if (p->dev_bytes == 0) p->dev_bytes = 256;
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->dev), p->dev_bytes);
     auto up = [&](size_t off, const void* src, size_t bytes) {
@@ -942,6 +963,7 @@ int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loc
     up(p->d_attiles, p->at_tiles.data(), p->at_tiles.size() * sizeof(PcTile));
     up(p->d_attiles64, p->at_tiles64.data(), p->at_tiles64.size() * sizeof(PcTile));
     up(p->d_atutts, p->at_utts.data(), p->at_utts.size() * sizeof(int32_t));
+    up(p->d_ppmap, L.pp_map.data(), L.pp_map.size() * sizeof(int32_t));
     if (e != cudaSuccess) {
         free_plan(p);
         return fail(h, LOCO_ERR_CUDA, std::string("loco_plan_create: ") + cudaGetErrorString(e));
@@ -1121,7 +1143,9 @@ int encode_with_plan(loco_handle* h, const loco_batch_plan& P, const void* input
     double* partial = reinterpret_cast<double*>(ws + L.off_partial);
     float* scale = reinterpret_cast<float*>(ws + L.off_scale);
     float* shift = reinterpret_cast<float*>(ws + L.off_shift);
+#ifdef LOCO_DEBUG
     const PcTile* pc_tiles = reinterpret_cast<const PcTile*>(P.dev + P.d_pctiles);
+#endif
     for (int i = 0; i < 6; ++i) {  // the 8 pad frames the last implicit-GEMM rows of layer i+1 may touch
         char nm[16];
         snprintf(nm, sizeof nm, "conv%d", i);
@@ -1162,9 +1186,12 @@ int encode_with_plan(loco_handle* h, const loco_batch_plan& P, const void* input
 #ifdef LOCO_DEBUG
     if (h->posconv_impl == 1)
         LAUNCH(CAT_POSCONV, launch_posconv(B("proj"), h->pos_w, h->pos_b, meta, n_utts, L.max_t6, B("pos_conv"), s), 1);
+    else if (h->posconv_impl == 2)
+        LAUNCH(CAT_POSCONV, launch_posconv_tc(B("proj"), h->pos_w_tc, h->pos_b, pc_tiles, (int)L.pc_tiles.size(), B("pos_conv"), s), 1);
     else
 #endif
-        LAUNCH(CAT_POSCONV, launch_posconv_tc(B("proj"), h->pos_w_tc, h->pos_b, pc_tiles, (int)L.pc_tiles.size(), B("pos_conv"), s), 1);
+        LAUNCH(CAT_POSCONV, launch_posconv_pp(B("proj"), h->pos_w_pp, h->pos_b, reinterpret_cast<const int32_t*>(P.dev + P.d_ppmap), L.n_vtiles,
+                                              B("pos_conv"), h->num_sms, s), 1);
     LAUNCH(CAT_ROWOPS, launch_prenet_ln(B("proj"), B("pos_conv"), h->sin_table, row_frame, B("x"), h->eln_w, h->eln_b, R6, s), 1);
     return run_transformer(h, P, ws, pooled_dev, hidden_dev, s);
 }

@@ -132,6 +132,19 @@ struct PcTile {      // one 128-frame output tile of one utterance
     int32_t t6;      // the utterance's frame count
     int32_t pad_;
 };
+// ---- positional conv on tcgen05, polyphase (posconv_pp.cu; the product kernel) -------------------
+// The batch on a virtual timeline: utterance after utterance, kPosPPHalo zero frames between neighbours; an item is
+// kPosPPTile consecutive timeline frames of one group.  vmap[kPosPPHalo + v] = row of timeline frame v in the [R6, 768]
+// buffers, or -1; it has n_vtiles * kPosPPTile + 2 * kPosPPHalo entries.
+constexpr int kPosPPTile = 512;
+constexpr int kPosPPHalo = 64;
+constexpr int kPosPPTaps = 139;      // taps per (group, channel chunk) in w_pp: 3 zero taps, the 128 taps, 8 zero taps
+int posconv_pp_init();
+// w_pp: [16 groups][6 in-chunks][kPosPPTaps][48 out][8 in] bf16
+int launch_posconv_pp(const bf16* h, const bf16* w_pp, const float* bias, const int32_t* vmap, int n_vtiles, bf16* pc, int num_sms,
+                      cudaStream_t s);
+
+// ---- positional conv on tcgen05, one output frame per accumulator row (posconv_tc.cu; debug cross-check) ----
 int posconv_tc_init();
 // w_tc: [16 groups][128 taps][6 in-chunks][48 out][8 in] bf16 -- one tap's block is a ready-made UMMA B operand.
 int launch_posconv_tc(const bf16* h, const bf16* w_tc, const float* bias, const PcTile* tiles, int n_tiles, bf16* pc,

@@ -53,6 +53,35 @@ def test_stage_by_stage_against_oracle_taps(debug_encoder, weights, ln_impl):
         off += T
 
 
+def test_positional_conv_kernels_agree(debug_encoder):
+    """The polyphase tcgen05 positional conv (product; four output frames per accumulator row, utterances sharing 512-frame
+    timeline tiles) against the one-phase tcgen05 kernel and the mma.sync kernel: same sums in another order.  The batch has
+    many short utterances per timeline tile, 1-frame utterances, and utterances that span two and three tiles."""
+    lengths = [400, 720, 6400] * 8 + [200000, 9000, 33000, 400, 330000, 48000, 64000] + [3200 + 160 * i for i in range(40)]
+    waves = H.make_waves(lengths, seed=77)
+    debug_encoder.debug_set("stop_after_layer", 0)
+    bufs = {}
+    try:
+        for impl in (0, 1, 2):
+            debug_encoder.debug_set("posconv_impl", impl)
+            _, _, info = H.run_encoder(debug_encoder, waves)
+            buf = debug_encoder.debug_buffer("pos_conv").float().cpu()
+            rows = []
+            for u in range(len(waves)):
+                r0, T = int(info["rows"][u]), int(info["frames"][u])
+                rows.append(buf[r0:r0 + T])
+            bufs[impl] = torch.cat(rows)
+    finally:
+        debug_encoder.debug_set("posconv_impl", 0)
+        debug_encoder.debug_set("stop_after_layer", -1)
+    assert torch.isfinite(bufs[0]).all()
+    for other in (1, 2):
+        assert H.rel_err(bufs[0], bufs[other]) < 1e-2, (other, H.rel_err(bufs[0], bufs[other]))
+        # bf16 outputs of fp32 sums taken in another order: all but a sliver of the values are the same bf16 number
+        same = float((bufs[0] == bufs[other]).float().mean())
+        assert same > 0.97, (other, same)
+
+
 def test_deferred_layernorm_equals_layernorm_kernels(debug_encoder):
     """The two formulations of the post-LN blocks (LayerNorm deferred into the GEMM epilogues, default; LayerNorm kernels)
     on a ragged batch: same function, different rounding points -- last_hidden_state within bf16 noise of each other."""
