@@ -51,6 +51,7 @@ def parse_args():
     p.add_argument("--no-stage-events", action="store_true", help="debug: time the steps without the per-launch CUDA events (no roofline)")
     p.add_argument("--gemm-impl", type=int, default=-1, help="debug: force GEMM kernel (0 single-CTA tcgen05, 2 CTA-pair tcgen05)")
     p.add_argument("--ln-impl", type=int, default=-1, help="debug: 0 deferred LayerNorm in the GEMM epilogues, 1 LayerNorm kernels")
+    p.add_argument("--conv0-impl", type=int, default=-1, help="debug: force conv0 kernel (0 tcgen05, 1 mma.sync)")
     p.add_argument("--posconv-impl", type=int, default=-1, help="debug: force positional-conv kernel (0 polyphase tcgen05, 1 mma.sync, 2 one-phase tcgen05)")
     p.add_argument("--attn-impl", type=int, default=-1, help="debug: force attention kernel (0 tcgen05, 1 mma.sync)")
     p.add_argument("--scaling", choices=["strong", "weak"], default="strong",
@@ -203,12 +204,14 @@ def main():
     import torch.distributed as dist
 
     strong = args.scaling == "strong"
-    dbg = args.attn_impl >= 0 or args.gemm_impl >= 0 or args.ln_impl >= 0 or args.posconv_impl >= 0       # kernel switches exist only in the LOCO_DEBUG build
+    dbg = args.attn_impl >= 0 or args.gemm_impl >= 0 or args.ln_impl >= 0 or args.posconv_impl >= 0 or args.conv0_impl >= 0       # kernel switches exist only in the LOCO_DEBUG build
     enc = LocoSpeechT5Encoder.from_state_dict(synth_state_dict(seed=1), device=dev, debug=dbg)
     if args.attn_impl >= 0:
         enc.debug_set("attn_impl", args.attn_impl)
     if args.gemm_impl >= 0:
         enc.debug_set("gemm_impl", args.gemm_impl)
+    if args.conv0_impl >= 0:
+        enc.debug_set("conv0_impl", args.conv0_impl)
     if args.posconv_impl >= 0:
         enc.debug_set("posconv_impl", args.posconv_impl)
     if args.ln_impl >= 0:

@@ -16,9 +16,10 @@
  *   - OWNERSHIP: the caller owns every device buffer it passes in (waveforms, outputs, workspace) -- the
  *     Python host allocates them through torch's caching allocator.  The handle owns only its weight copies.
  *   - STREAMS: all work is enqueued on the caller's stream (a cudaStream_t passed as void*).  Host synchronisation happens
- *     only in loco_encode_host (which must hand host memory back), in loco_sync_check, and the FIRST time loco_encode /
- *     loco_encode_text see a batch geometry (they build and cache its plan; see loco_plan_create).  Asynchronous CUDA errors
- *     surface at the next call or at loco_sync_check.
+ *     only in loco_encode_host (which must hand host memory back), in loco_sync_check and in loco_plan_create.  The FIRST time
+ *     loco_encode / loco_encode_text see a batch geometry they build and cache its plan (host work + cudaMalloc) and upload it
+ *     with one asynchronous copy on the caller's stream, ordered before the encode -- the device is not synchronised, so a
+ *     queue of first-time encodes keeps the GPU busy.  Asynchronous CUDA errors surface at the next call or at loco_sync_check.
  *   - a handle is bound to one device, is not thread-safe; use one handle per rank.
  */
 #ifndef LOCO_ASR_H_
@@ -130,7 +131,8 @@ LOCO_API int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n
  * synchronisation -- so it may be captured into a CUDA graph: capture one call per bucket, then replay the graph after
  * refilling the same input buffer (same lengths).  The caller still owns input, outputs and workspace (loco_plan_info's
  * workspace_bytes; any alignment).  A plan may be used any number of times, from one handle, until loco_plan_destroy.
- * loco_encode / loco_encode_text are exactly loco_plan_create (cached per geometry, up to 256 of them) + loco_encode_planned. */
+ * loco_encode / loco_encode_text are loco_plan_create (cached per geometry, up to 256 of them; uploaded asynchronously on the
+ * encoding stream instead of synchronously) + loco_encode_planned. */
 typedef struct loco_batch_plan loco_batch_plan;
 LOCO_API int loco_plan_create(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loco_batch_plan** out);
 LOCO_API int loco_plan_info(const loco_batch_plan* plan, int32_t* frames, int32_t* rows, int64_t* total_frames, size_t* workspace_bytes);
@@ -197,11 +199,11 @@ LOCO_API int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_
 
 /* ---- debug / test hooks (not part of the product surface) -------------------------------------------
  * The product library (libloco_asr.so) contains only the product kernels; loco_debug_set fails on it.  The cross-check
- * kernels (SIMT GEMM, single-CTA tcgen05 GEMM, mma.sync and one-phase tcgen05 positional conv, mma.sync attention, stand-alone LayerNorm path) and the
+ * kernels (SIMT GEMM, single-CTA tcgen05 GEMM, mma.sync conv0, mma.sync and one-phase tcgen05 positional conv, mma.sync attention, stand-alone LayerNorm path) and the
  * knobs that select them are compiled only with -DLOCO_DEBUG into libloco_asr_debug.so, which the unit tests load. */
 LOCO_API int loco_is_debug_build(void);
 /* name: "gemm_impl" (2 = tcgen05 CTA pair, cta_group::2 [default], 0 = tcgen05 single CTA, 1 = SIMT reference), "posconv_impl" (0 = polyphase tcgen05 [default],
- * 1 = mma.sync cross-check, 2 = one-phase tcgen05 cross-check), "ln_impl" (0 = the transformer layers' LayerNorms deferred into the GEMM epilogues [default, needs gemm_impl 2],
+ * 1 = mma.sync cross-check, 2 = one-phase tcgen05 cross-check), "conv0_impl" (0 = tcgen05 [default], 1 = mma.sync cross-check), "ln_impl" (0 = the transformer layers' LayerNorms deferred into the GEMM epilogues [default, needs gemm_impl 2],
  * 1 = LayerNorm kernels), "attn_impl" (-1 = per utterance by its own frame count [default], 0 = tcgen05, 1 = mma.sync), "attn_tc_min_frames" / "attn_tc_lo" / "attn_tc_hi" (the frame ranges that select the tcgen05 kernel), "stop_after_layer"
  * (-1 = run all).  */
 LOCO_API int loco_debug_set(loco_handle* h, const char* name, int64_t value);

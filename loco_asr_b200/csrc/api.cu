@@ -52,6 +52,8 @@ struct Layout {
     int max_t0 = 0, max_t6 = 0, max_slot6 = 0, chunks = 1;
     std::vector<UttMeta> meta;
     std::vector<PcTile> pc_tiles;
+    std::vector<int32_t> c0_tile_start;         // conv0: first 128-frame tile of each utterance (n_utts + 1 entries; conv0_tc.cu)
+    size_t off_wfold = 0;                       // conv0: per-utterance folded weights, kConv0FoldBytes each
     std::vector<int32_t> pp_map;                // positional conv: timeline frame -> row (internal.h, posconv_pp.cu)
     int n_vtiles = 0;
     size_t off_stats1 = 0, off_stats2 = 0;      // deferred LayerNorm: row statistics of attn_res / ffn_res, [R6, 6, 2] fp32
@@ -76,7 +78,12 @@ struct loco_batch_plan {
     std::vector<int32_t> at_utts;               // LOCO_DEBUG builds: utterances routed to the mma.sync cross-check kernel
     int at_ms_max_t6 = 0;
     uint8_t* dev = nullptr;                     // [meta | pc_tiles | at_tiles | at_utts | pp_map]
-    size_t d_ppmap = 0;
+    size_t d_ppmap = 0, d_c0tiles = 0;
+    // plans made on behalf of loco_encode upload their block asynchronously on the encoding stream (no device synchronisation in
+    // the middle of a queue of encodes): pinned staging copy kept for the plan's life, event for encodes on other streams
+    uint8_t* staging = nullptr;
+    cudaEvent_t uploaded = nullptr;
+    cudaStream_t upload_stream = nullptr;
     size_t d_meta = 0, d_pctiles = 0, d_attiles = 0, d_attiles64 = 0, d_atutts = 0, dev_bytes = 0;
     int device = 0;
     bool cached = false;                        // owned by the handle's plan cache (loco_encode), not by the caller
@@ -117,7 +124,8 @@ struct loco_handle {
     bool head_set = false;
     // debug
     int gemm_impl = 2;          // 2 = tcgen05 CTA pair [default], 0 = tcgen05 single CTA, 1 = SIMT reference
-    int posconv_impl = 0;
+    int posconv_impl = 0;       // 0 = polyphase tcgen05 [default], 1 = mma.sync, 2 = one-phase tcgen05
+    int conv0_impl = 0;         // 0 = tcgen05 [default], 1 = mma.sync
     int ln_impl = 0;            // 0 = LayerNorms of the transformer layers deferred into the GEMM epilogues [default], 1 = LayerNorm kernels
     int attn_impl = 0;          // 0 = tcgen05 [default, the only product kernel], 1 = mma.sync cross-check, -1 = by length (round-1 routing)
     bool attn_p2 = true;        // utterances shorter than attn_p2_max_frames go to the two-pipeline tcgen05 kernel (attention_p2.cu),
@@ -393,6 +401,9 @@ int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L)
         if (slot > L->max_slot6) L->max_slot6 = slot;
     }
     if ((row << 6) > (int64_t)INT32_MAX / 2) return fail(h, LOCO_ERR_INVALID, "batch too large: more than 2^30 conv0 frames");
+    L->c0_tile_start.resize((size_t)n_utts + 1);
+    L->c0_tile_start[0] = 0;
+    for (int u = 0; u < n_utts; ++u) L->c0_tile_start[u + 1] = L->c0_tile_start[u] + (L->meta[u].slot6 + 1) / 2;     // slot6 * 64 frames in 128-frame tiles
     {
         // positional conv timeline: utterances back to back with kPosPPHalo zero frames between neighbours
         const int64_t total = out_row + (int64_t)n_utts * kPosPPHalo;
@@ -419,6 +430,7 @@ int make_layout(loco_handle* h, const int32_t* n_samples, int n_utts, Layout* L)
     L->off_partial = take((size_t)n_utts * L->chunks * 65 * sizeof(double));
     L->off_scale = take((size_t)n_utts * kConvDim * sizeof(float));
     L->off_shift = take((size_t)n_utts * kConvDim * sizeof(float));
+    L->off_wfold = take((size_t)n_utts * kConv0FoldBytes);
     L->off_stats1 = take((size_t)L->R6 * 2 * kStatSlots * sizeof(float));
     L->off_stats2 = take((size_t)L->R6 * 2 * kStatSlots * sizeof(float));
     L->off_rowframe = take((size_t)L->R6 * sizeof(int32_t));
@@ -612,8 +624,9 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
     if (!rc) rc = attention_tc_init();
     if (!rc) rc = attention_p2_init();
     if (!rc) rc = posconv_pp_init();
-    if (!rc) rc = frontend_init();
+    if (!rc) rc = conv0_tc_init();
 #ifdef LOCO_DEBUG
+    if (!rc) rc = conv0_mma_init();
     if (!rc) rc = posconv_tc_init();
     if (!rc) rc = gemm_tc_init();
     if (!rc) rc = attention_init();
@@ -873,15 +886,18 @@ uint64_t hash_lengths(int kind, const int32_t* v, int n) {
 
 void free_plan(loco_batch_plan* p) {
     if (!p) return;
-    if (p->dev) {
-        cudaSetDevice(p->device);
-        cudaFree(p->dev);
-    }
+    if (p->dev || p->staging || p->uploaded) cudaSetDevice(p->device);
+    if (p->dev) cudaFree(p->dev);             // waits for work that may still read the block
+    if (p->staging) cudaFreeHost(p->staging);
+    if (p->uploaded) cudaEventDestroy(p->uploaded);
     delete p;
 }
 
-// Geometry + work lists + the device block.  Synchronous (cudaMalloc / cudaMemcpy): plan outside captures and hot loops.
-int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loco_batch_plan** out) {
+// Geometry + work lists + the device block.  `async_stream` null: synchronous upload (loco_plan_create; plan outside captures
+// and hot loops).  Otherwise the block is copied from a pinned staging buffer on that stream, ordered before the encode that
+// follows on it -- the device is never synchronised, so a queue of first-time encodes keeps the GPU busy.
+int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loco_batch_plan** out, bool async = false,
+               cudaStream_t async_stream = nullptr) {
     if (!h->finalized) return fail(h, LOCO_ERR_STATE, "plan before loco_finalize_weights");
     if (kind == 0 && !h->has_speech) return fail(h, LOCO_ERR_STATE, "this handle was loaded without the speech prenet (text-only weights)");
     if (kind == 1 && !h->has_text) return fail(h, LOCO_ERR_STATE, "this handle was loaded without the text prenet (prenet.embed_tokens.weight)");
@@ -953,10 +969,14 @@ int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loc
     p->d_attiles64 = place(p->at_tiles64.size() * sizeof(PcTile));
     p->d_atutts = place(p->at_utts.size() * sizeof(int32_t));
     p->d_ppmap = place(L.pp_map.size() * sizeof(int32_t));
+    p->d_c0tiles = place(L.c0_tile_start.size() * sizeof(int32_t));
     if (p->dev_bytes == 0) p->dev_bytes = 256;
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->dev), p->dev_bytes);
+    if (async && e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&p->staging), p->dev_bytes);
     auto up = [&](size_t off, const void* src, size_t bytes) {
-        if (e == cudaSuccess && bytes) e = cudaMemcpy(p->dev + off, src, bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess || !bytes) return;
+        if (async) memcpy(p->staging + off, src, bytes);
+        else e = cudaMemcpy(p->dev + off, src, bytes, cudaMemcpyHostToDevice);
     };
     up(p->d_meta, L.meta.data(), (size_t)n_utts * sizeof(UttMeta));
     up(p->d_pctiles, L.pc_tiles.data(), L.pc_tiles.size() * sizeof(PcTile));
@@ -964,6 +984,13 @@ int build_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, loc
     up(p->d_attiles64, p->at_tiles64.data(), p->at_tiles64.size() * sizeof(PcTile));
     up(p->d_atutts, p->at_utts.data(), p->at_utts.size() * sizeof(int32_t));
     up(p->d_ppmap, L.pp_map.data(), L.pp_map.size() * sizeof(int32_t));
+    up(p->d_c0tiles, L.c0_tile_start.data(), L.c0_tile_start.size() * sizeof(int32_t));
+    if (async) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p->dev, p->staging, p->dev_bytes, cudaMemcpyHostToDevice, async_stream);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(p->uploaded, async_stream);
+        p->upload_stream = async_stream;
+    }
     if (e != cudaSuccess) {
         free_plan(p);
         return fail(h, LOCO_ERR_CUDA, std::string("loco_plan_create: ") + cudaGetErrorString(e));
@@ -981,8 +1008,8 @@ void clear_plan_cache(loco_handle* h) {
     h->last_plan = nullptr;
 }
 
-// The plan of this batch, built on first sight (that call synchronises the device once) and reused afterwards.
-int cached_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, const loco_batch_plan** out) {
+// The plan of this batch, built on first sight (uploaded on the encoding stream, no synchronisation) and reused afterwards.
+int cached_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, const loco_batch_plan** out, cudaStream_t s) {
     const uint64_t key = hash_lengths(kind, lengths, n_utts);
     auto it = h->plan_index.find(key);
     if (it != h->plan_index.end()) {
@@ -999,7 +1026,9 @@ int cached_plan(loco_handle* h, int kind, const int32_t* lengths, int n_utts, co
         h->plan_index.erase(it);
     }
     loco_batch_plan* p = nullptr;
-    int rc = build_plan(h, kind, lengths, n_utts, &p);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);           // a capture cannot hold the allocation anyway: the synchronous form reports it
+    int rc = build_plan(h, kind, lengths, n_utts, &p, cap == cudaStreamCaptureStatusNone, s);
     if (rc) return rc;
     p->cached = true;
     h->plan_lru.push_front(p);
@@ -1125,6 +1154,7 @@ int encode_with_plan(loco_handle* h, const loco_batch_plan& P, const void* input
         return fail(h, LOCO_ERR_WORKSPACE, "workspace too small: need " + std::to_string(L.bytes + kWsSlack) +
                                                " bytes (the plan's workspace_bytes), got " + std::to_string(workspace_bytes));
     CK(cudaSetDevice(h->device));
+    if (P.uploaded && s != P.upload_stream) CK(cudaStreamWaitEvent(s, P.uploaded, 0));
     prof_break(h);
     h->last_plan = &P;
     h->last_ws = ws;
@@ -1154,8 +1184,15 @@ int encode_with_plan(loco_handle* h, const loco_batch_plan& P, const void* input
     }
     prof_break(h);
     // ---- conv feature encoder -----------------------------------------------------------------------
-    LAUNCH(CAT_FRONTEND, launch_wave_stats(wave_dev, meta, n_utts, L.chunks, h->w0, h->gn_w, h->gn_b, partial, scale, shift, s), 2);
-    LAUNCH(CAT_FRONTEND, launch_conv0(wave_dev, meta, n_utts, L.max_slot6 << 6, h->w0, scale, shift, B("conv0"), s), 1);
+    bf16* wfold = reinterpret_cast<bf16*>(ws + L.off_wfold);
+    LAUNCH(CAT_FRONTEND, launch_wave_stats(wave_dev, meta, n_utts, L.chunks, h->w0, h->gn_w, h->gn_b, partial, scale, shift, wfold, s), 2);
+#ifdef LOCO_DEBUG
+    if (h->conv0_impl == 1)
+        LAUNCH(CAT_FRONTEND, launch_conv0(wave_dev, meta, n_utts, L.max_slot6 << 6, h->w0, scale, shift, B("conv0"), s), 1);
+    else
+#endif
+        LAUNCH(CAT_FRONTEND, launch_conv0_tc(wave_dev, meta, reinterpret_cast<const int32_t*>(P.dev + P.d_c0tiles), n_utts, L.c0_tile_start[n_utts],
+                                             wfold, B("conv0"), L.R6 << 6, h->num_sms, s), 1);
     for (int i = 1; i < 7; ++i) {
         char in[16], out[16];
         snprintf(in, sizeof in, "conv%d", i - 1);
@@ -1265,7 +1302,7 @@ int loco_encode(loco_handle* h, const float* wave_dev, const int32_t* n_samples,
     if (!wave_dev || !n_samples || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode: null argument");
     return guarded(h, "loco_encode", [&]() -> int {
         const loco_batch_plan* plan = nullptr;
-        int rc = cached_plan(h, 0, n_samples, n_utts, &plan);
+        int rc = cached_plan(h, 0, n_samples, n_utts, &plan, reinterpret_cast<cudaStream_t>(stream));
         if (rc) return rc;
         return encode_with_plan(h, *plan, wave_dev, pooled_dev, hidden_dev, workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
     });
@@ -1291,7 +1328,7 @@ int loco_encode_host(loco_handle* h, const float* wave_host, const int32_t* n_sa
     if (!h->finalized) return fail(h, LOCO_ERR_STATE, "loco_encode_host before loco_finalize_weights");
     return guarded(h, "loco_encode_host", [&]() -> int {
         const loco_batch_plan* plan = nullptr;
-        int rc = cached_plan(h, 0, n_samples, n_utts, &plan);
+        int rc = cached_plan(h, 0, n_samples, n_utts, &plan, reinterpret_cast<cudaStream_t>(stream));
         if (rc) return rc;
         const Layout& L = plan->L;
         const size_t wave_bytes = (size_t)L.total_samples * sizeof(float);
@@ -1340,7 +1377,7 @@ int loco_encode_text(loco_handle* h, const int32_t* tokens_dev, const int32_t* n
     if (!tokens_dev || !n_tokens || !pooled_dev || !workspace_dev) return fail(h, LOCO_ERR_INVALID, "loco_encode_text: null argument");
     return guarded(h, "loco_encode_text", [&]() -> int {
         const loco_batch_plan* plan = nullptr;
-        int rc = cached_plan(h, 1, n_tokens, n_utts, &plan);
+        int rc = cached_plan(h, 1, n_tokens, n_utts, &plan, reinterpret_cast<cudaStream_t>(stream));
         if (rc) return rc;
         return encode_with_plan(h, *plan, tokens_dev, pooled_dev, hidden_dev, workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
     });
@@ -1424,6 +1461,7 @@ int loco_debug_set(loco_handle* h, const char* name, int64_t value) {
 #ifdef LOCO_DEBUG
     if (!strcmp(name, "gemm_impl")) h->gemm_impl = (int)value;
     else if (!strcmp(name, "posconv_impl")) h->posconv_impl = (int)value;
+    else if (!strcmp(name, "conv0_impl")) h->conv0_impl = (int)value;
     else if (!strcmp(name, "ln_impl")) h->ln_impl = (int)value;
     else if (!strcmp(name, "attn_impl")) h->attn_impl = (int)value;
     else if (!strcmp(name, "attn_p2")) h->attn_p2 = value != 0;

@@ -90,11 +90,18 @@ struct UttMeta {          // per-utterance geometry, device-resident
     int32_t out_row;      // first row in the compact hidden_out buffer (prefix sum of t6)
 };
 
-int frontend_init();
 int wave_stats_chunks(int max_t0);
 int launch_wave_stats(const float* wave, const UttMeta* meta, int n_utts, int chunks, const float* w0 /*[512,10]*/,
                       const float* gn_w, const float* gn_b, double* partial /*[n, chunks, 65]*/, float* scale /*[n,512]*/,
-                      float* shift /*[n,512]*/, cudaStream_t s);
+                      float* shift /*[n,512]*/, bf16* wfold /*[n, kConv0FoldBytes] or null*/, cudaStream_t s);
+// conv0 + GroupNorm + GELU on tcgen05 (conv0_tc.cu; the product kernel).  wfold: per utterance the K = 48 split-GEMM B operand
+// gn_finalize_kernel wrote; tile_start[u] = first 128-frame tile of utterance u in the batch's tile order (n_utts + 1 entries).
+constexpr int kConv0FoldBytes = 6 * 512 * 16;
+int conv0_tc_init();
+int launch_conv0_tc(const float* wave, const UttMeta* meta, const int32_t* tile_start, int n_utts, int n_tiles, const bf16* wfold,
+                    bf16* out /*[out_rows, 512]*/, int64_t out_rows, int num_sms, cudaStream_t s);
+// mma.sync version (conv0_mma.cu; debug cross-check)
+int conv0_mma_init();
 int launch_conv0(const float* wave, const UttMeta* meta, int n_utts, int max_slot0, const float* w0, const float* scale,
                  const float* shift, bf16* out /*[R0, 512]*/, cudaStream_t s);
 

@@ -49,10 +49,10 @@ def test_product_library_ships_only_product_kernels():
     if not prod:
         pytest.skip("cuobjdump not available")
     joined = " ".join(sorted(prod))
-    for name in ("gemm_simt", "gemm_tc_kernel", "posconv_kernel", "posconv_tc_kernel", "attention_kernel"):
+    for name in ("gemm_simt", "gemm_tc_kernel", "posconv_kernel", "posconv_tc_kernel", "conv0_mma_kernel", "attention_kernel"):
         assert not re.search(r"\d+%s" % name, joined), name
         assert re.search(r"\d+%s" % name, " ".join(sorted(dbg))), name
-    for name in ("gemm_tc2_kernel", "attention_tc_kernel", "posconv_pp_kernel", "conv0_mma_kernel", "final_ln_pool_kernel"):
+    for name in ("gemm_tc2_kernel", "attention_tc_kernel", "posconv_pp_kernel", "conv0_tc_kernel", "final_ln_pool_kernel"):
         assert re.search(name, joined), name
 
 

@@ -53,6 +53,35 @@ def test_stage_by_stage_against_oracle_taps(debug_encoder, weights, ln_impl):
         off += T
 
 
+def test_conv0_kernels_agree(debug_encoder):
+    """conv0 + GroupNorm + GELU: the tcgen05 kernel (product; K = 48 split GEMM with the GroupNorm shift in the padding taps)
+    against the mma.sync kernel (shift as the fp32 initial accumulator) on a ragged batch -- utterances of one tile, of many
+    tiles, and with slot padding frames (which both must write as zeros)."""
+    lengths = [400, 720, 6400, 200000, 9000, 33000, 401, 330000, 48000, 64000, 1279, 1280] + [3200 + 170 * i for i in range(30)]
+    waves = H.make_waves(lengths, seed=78)
+    debug_encoder.debug_set("stop_after_layer", 0)
+    bufs = {}
+    try:
+        for impl in (0, 1):
+            debug_encoder.debug_set("conv0_impl", impl)
+            _, _, info = H.run_encoder(debug_encoder, waves)
+            buf = debug_encoder.debug_buffer("conv0").float().cpu()
+            rows = []
+            for u in range(len(waves)):
+                r0 = int(info["rows"][u]) << 6
+                r1 = (int(info["rows"][u + 1]) << 6) if u + 1 < len(waves) else buf.shape[0]
+                rows.append(buf[r0:r1])              # the whole slot: valid frames and the zero padding frames after them
+            bufs[impl] = torch.cat(rows)
+    finally:
+        debug_encoder.debug_set("conv0_impl", 0)
+        debug_encoder.debug_set("stop_after_layer", -1)
+    assert torch.isfinite(bufs[0]).all()
+    assert H.rel_err(bufs[0], bufs[1]) < 1e-2, H.rel_err(bufs[0], bufs[1])
+    same = float((bufs[0] == bufs[1]).float().mean())
+    assert same > 0.99, same
+    assert torch.equal(bufs[0] == 0, bufs[1] == 0) or float(((bufs[0] == 0) != (bufs[1] == 0)).float().mean()) < 1e-4
+
+
 def test_positional_conv_kernels_agree(debug_encoder):
     """The polyphase tcgen05 positional conv (product; four output frames per accumulator row, utterances sharing 512-frame
     timeline tiles) against the one-phase tcgen05 kernel and the mma.sync kernel: same sums in another order.  The batch has
