@@ -12,9 +12,9 @@ from collections import OrderedDict
 
 raw, prefix = sys.argv[1], sys.argv[2]
 note = sys.argv[3] if len(sys.argv) > 3 else ""
-KERNELS = "row_frames|wave_moments|gn_finalize|conv0_mma|gemm_tc|layernorm_kernel|posconv_tc|prenet_ln|attention|final_ln_pool"
+KERNELS = "row_frames|wave_moments|gn_finalize|conv0_tc|gemm_tc|layernorm_kernel|posconv_pp|prenet_ln|attention|final_ln_pool"
 CMD = ("ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-       f"-k 'regex:{KERNELS}' --launch-skip 75 -c 175 --csv python bench.py --steps 2 --warmup 1 --e2e-steps 1 --no-cpu-baseline")
+       f"-k 'regex:{KERNELS}' --launch-skip 70 -c 210 --csv python bench.py --steps 2 --warmup 1 --e2e-steps 1 --no-cpu-baseline")
 
 
 def short(name):
