@@ -160,10 +160,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u);
                     const uint32_t full = smem_u32(&bars->full[stage]);
-                    if (rank == 0) mbar_arrive_expect_tx(full, 2 * STAGE_BYTES);       // both CTAs' A tile and B half
+#ifdef G2_EXP_SKIP_B      // measurement only (wrong results): every other k-block reuses the stale weight half -> 25 % less SM ingest
+                    const bool skip_b = (kb & 1) != 0;
+#else
+                    constexpr bool skip_b = false;
+#endif
+                    if (rank == 0) mbar_arrive_expect_tx(full, skip_b ? 2 * A_STAGE_BYTES : 2 * STAGE_BYTES);       // both CTAs' A tile and B half
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     tma_load_2d_pair(sa, &tma_a, full & kPeerMask, kb * BK, m0);
-                    tma_load_2d_pair(sa + A_STAGE_BYTES, &tma_b, full & kPeerMask, kb * BK, n0);
+                    if (!skip_b) tma_load_2d_pair(sa + A_STAGE_BYTES, &tma_b, full & kPeerMask, kb * BK, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
