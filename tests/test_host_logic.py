@@ -137,3 +137,88 @@ def test_exp2_polynomial_error_bound():
     assert np.isfinite(got).all() and (got > 0).all()
     assert (np.abs(got.astype(np.float64) / ref - 1)).max() < 1e-4
     assert got[np.isneginf(x)][0] < 1e-37                     # masked keys: 2^-125, nothing against a row sum >= 1
+
+
+def test_polyphase_positional_conv_algebra():
+    """The index algebra of posconv_pp.cu restated in numpy for one group: utterances on a timeline with 64 zero frames between
+    them, the window de-interleaved by frame phase, weights as [3 zero taps | 128 taps | zero taps], step j multiplying phase
+    array j % 4 (rows shifted by j // 4) with the four taps j-3 .. j side by side, column block q holding output phase 3 - q --
+    against the reference's Conv1d(k = 128, padding = 64) with the last frame dropped (HF modeling_speecht5.py:355-397, 445-453)."""
+    rng = np.random.default_rng(5)
+    C, K, P, ROWS, TILE, HALO = 6, 128, 4, 128, 512, 64            # 6 channels instead of 48: the algebra does not depend on it
+    lens = [1, 37, 150, 700, 64]
+    xs = [rng.standard_normal((t, C)) for t in lens]
+    w = rng.standard_normal((K, C, C)) * 0.1                        # [tap][in][out]
+    n_steps = K + P - 1
+    wp = np.zeros((n_steps + 8, C, C))
+    wp[3:3 + K] = w
+    total = sum(lens) + HALO * len(lens)
+    n_vt = (total + TILE - 1) // TILE
+    vmap = -np.ones(n_vt * TILE + 2 * HALO, dtype=np.int64)         # vmap[HALO + v] = packed row of timeline frame v
+    packed = np.concatenate(xs)
+    pos, row = HALO, 0
+    for t in lens:
+        vmap[pos:pos + t] = np.arange(row, row + t)
+        pos += t + HALO
+        row += t
+    out = np.zeros_like(packed)
+    for vt in range(n_vt):
+        win = np.zeros((ROWS * P + K, C))                           # timeline frames vt*TILE - 64 .. + 575
+        idx = vmap[vt * TILE: vt * TILE + ROWS * P + K]
+        win[idx >= 0] = packed[idx[idx >= 0]]
+        phase = [win[b::P] for b in range(P)]                       # x_b[r] = X[4 r + b], 160 rows each
+        acc = np.zeros((ROWS, P * C))
+        for j in range(n_steps):
+            a = phase[j % P][j // P: j // P + ROWS]                 # row s = frame 4 s + j - 64
+            b = np.concatenate([wp[j + q] for q in range(P)], axis=1)        # [in][4 * out]: taps j-3+q
+            acc += a @ b
+        for s in range(ROWS):
+            for q in range(P):
+                r = vmap[HALO + vt * TILE + P * s + (P - 1 - q)]
+                if r >= 0:
+                    out[r] = acc[s, q * C:(q + 1) * C]
+    ref, row = np.zeros_like(packed), 0
+    for x in xs:
+        xt = torch.from_numpy(x.T.copy())[None]                     # [1, C, T]
+        wt = torch.from_numpy(np.transpose(w, (2, 1, 0)).copy())    # [out, in, tap]
+        y = torch.nn.functional.conv1d(xt, wt, padding=K // 2)[0, :, :x.shape[0]]     # SamePad: drop the last frame
+        ref[row:row + x.shape[0]] = y.T.numpy()
+        row += x.shape[0]
+    assert np.abs(out - ref).max() < 1e-10
+
+
+def test_conv0_split_gemm_algebra():
+    """conv0_tc.cu's K = 48 operand layout restated in numpy: A = [x_hi 1 0.. | x_lo 0.. | x_hi 1 0..], B = [w'_hi sh_hi | w'_hi 0 |
+    w'_lo sh_lo] with bf16 operands and fp32 accumulation reproduces scale * conv(x, w) + shift to ~2^-16 -- the 3-term split and
+    the GroupNorm shift carried in the padding taps."""
+    def bf16(a):
+        return torch.from_numpy(np.asarray(a, dtype=np.float32)).bfloat16().float().numpy()
+    rng = np.random.default_rng(7)
+    n_frames, n_ch = 300, 64
+    x = rng.standard_normal(5 * n_frames + 5).astype(np.float32) * 0.3
+    w = (rng.standard_normal((n_ch, 10)) * 0.2).astype(np.float32)
+    scale = (0.5 + rng.random(n_ch) * 3).astype(np.float32)
+    shift = rng.standard_normal(n_ch).astype(np.float32)
+    taps = np.stack([x[5 * f: 5 * f + 10] for f in range(n_frames)])          # [frames, 10]
+    x_hi = bf16(taps)
+    x_lo = bf16(taps - x_hi)
+    wf = w * scale[:, None]
+    w_hi = bf16(wf)
+    w_lo = bf16(wf - w_hi)
+    sh_hi = bf16(shift)
+    sh_lo = bf16(shift - sh_hi)
+    A = np.zeros((n_frames, 48), dtype=np.float32)
+    B = np.zeros((n_ch, 48), dtype=np.float32)
+    A[:, 0:10], A[:, 10] = x_hi, 1.0
+    A[:, 16:26] = x_lo
+    A[:, 32:42], A[:, 42] = x_hi, 1.0
+    B[:, 0:10], B[:, 10] = w_hi, sh_hi
+    B[:, 16:26] = w_hi
+    B[:, 32:42], B[:, 42] = w_lo, sh_lo
+    got = A.astype(np.float64) @ B.T.astype(np.float64)
+    ref = taps.astype(np.float64) @ wf.T.astype(np.float64) + shift[None, :].astype(np.float64)
+    bound = 2.0 ** -15 * (np.abs(taps).astype(np.float64) @ np.abs(wf.T).astype(np.float64) + np.abs(shift)[None, :])
+    assert np.all(np.abs(got - ref) <= bound)
+    # one bf16 pass alone is two orders worse: the split is what buys fp32-like accuracy
+    one = x_hi.astype(np.float64) @ w_hi.T.astype(np.float64) + shift[None, :]
+    assert np.abs(one - ref).max() > 30 * np.abs(got - ref).max()
