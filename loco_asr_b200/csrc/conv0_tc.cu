@@ -73,7 +73,6 @@ struct TileWalk {
     }
 };
 
-__device__ __forceinline__ uint32_t bf16_bits(float x) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x)); }
 
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv0_tc_kernel(const float* __restrict__ wave, const UttMeta* __restrict__ meta, const int32_t* __restrict__ tile_start, int n_utts,
