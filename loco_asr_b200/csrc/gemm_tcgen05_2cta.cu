@@ -99,6 +99,17 @@ struct LnArgs {                       // deferred-LayerNorm operands (GemmArgs o
     float* stats_out;
 };
 
+// Tile order: N fastest -- the CTA pairs that run at the same time share A row blocks (read from DRAM once) and the whole weight
+// matrix stays L2-hot.  -DG2_RASTER_N_SLOW (measurement only) walks M fastest instead: a pair keeps one weight tile and its epilogue
+// vectors for consecutive tiles, but A is streamed from DRAM once per N tile (profiles/r04m_gemm_raster_experiment.txt).
+#ifdef G2_RASTER_N_SLOW
+#define TILE_M(t) ((t) % n_tiles_m)
+#define TILE_N(t) ((t) / n_tiles_m)
+#else
+#define TILE_M(t) ((t) / n_tiles_n)
+#define TILE_N(t) ((t) % n_tiles_n)
+#endif
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -155,8 +166,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-                const int m0 = (tile / n_tiles_n) * (2 * BM) + (int)rank * BM;
-                const int n0 = (tile % n_tiles_n) * BN + (int)rank * (BN / 2);
+                const int m0 = TILE_M(tile) * (2 * BM) + (int)rank * BM;
+                const int n0 = TILE_N(tile) * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u);
                     const uint32_t full = smem_u32(&bars->full[stage]);
@@ -211,8 +222,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-            const int m0 = (tile / n_tiles_n) * (2 * BM) + (int)rank * BM + q * 32;
-            const int n0 = (tile % n_tiles_n) * BN + half * (BN / 2);
+            const int m0 = TILE_M(tile) * (2 * BM) + (int)rank * BM + q * 32;
+            const int n0 = TILE_N(tile) * BN + half * (BN / 2);
             if (kRes && PANELS == 2) {
                 // both residual panels of this warp's 32 x 128 slice, fetched while the tile's MMAs still run
                 if (lane == 0) {
@@ -347,7 +358,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                 const float mean_p = sum * (1.0f / 128.f);
                 const int row = m0 + lane;
                 if (row < M)
-                    *reinterpret_cast<float2*>(ln.stats_out + (int64_t)row * (2 * kStatSlots) + 2 * ((tile % n_tiles_n) * 2 + half)) =
+                    *reinterpret_cast<float2*>(ln.stats_out + (int64_t)row * (2 * kStatSlots) + 2 * (TILE_N(tile) * 2 + half)) =
                         make_float2(mean_p, fmaxf(sq - sum * mean_p, 0.f));
             }
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
