@@ -132,7 +132,7 @@ int launch_row_frames(const UttMeta* meta, int n_utts, int max_slot6, int32_t* r
 int launch_text_prenet_ln(const int32_t* tokens, const float* embed /*[vocab, 768]*/, const float* pe /*[positions, 768]*/, float alpha,
                           int vocab, const int32_t* row_frame, bf16* y, const float* gamma, const float* beta, int rows, cudaStream_t s);
 
-// ---- positional conv on tcgen05 (posconv_tc.cu) ------------------------------------------------
+// ---- 128- / 64-frame tiles of one utterance: attention work lists and the one-phase positional conv (posconv_tc.cu) ----
 struct PcTile {      // one 128-frame output tile of one utterance
     int32_t row0;    // row of the tile's first frame in the [R6, 768] buffers
     int32_t f0;      // that frame's index inside its utterance

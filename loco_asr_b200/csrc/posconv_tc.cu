@@ -1,5 +1,6 @@
-// Grouped positional convolution on tcgen05 (product path; posconv.cu keeps the mma.sync version as a debug
-// cross-check).  SpeechT5PositionalConvEmbedding + SamePad, HF modeling_speecht5.py:355-397, 445-453:
+// Grouped positional convolution on tcgen05, one output frame per accumulator row (the product kernel until the polyphase
+// form of posconv_pp.cu replaced it; now LOCO_DEBUG builds only, "posconv_impl" = 2, a cross-check with the same summation
+// order).  SpeechT5PositionalConvEmbedding + SamePad, HF modeling_speecht5.py:355-397, 445-453:
 // Conv1d(768 -> 768, k = 128, padding 64, groups 16), weight-norm folded at load, last frame dropped, + bias, GELU.
 //
 // Per group: out[T, 48] = X_toeplitz[T, 128*48] * W_g[128*48, 48].  The Toeplitz operand is never built.  A CTA
