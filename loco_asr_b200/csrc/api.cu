@@ -1123,8 +1123,9 @@ static int run_transformer(loco_handle* h, const loco_batch_plan& P, uint8_t* ws
     const int R6 = (int)L.R6;
     const PcTile* at_tiles_dev = reinterpret_cast<const PcTile*>(P.dev + P.d_attiles);
     const PcTile* at_tiles64_dev = reinterpret_cast<const PcTile*>(P.dev + P.d_attiles64);
+#ifdef LOCO_DEBUG
     const int32_t* at_utts_dev = reinterpret_cast<const int32_t*>(P.dev + P.d_atutts);
-    (void)at_utts_dev;
+#endif
     // slot padding rows of ctx are never written by the attention kernels; keep them finite (zero) so they stay finite
     // through every later layer -- the tcgen05 attention multiplies masked (P = 0) key rows into O, and 0 * NaN = NaN
     CK(cudaMemsetAsync(ws + L.bufs.at("ctx").off, 0, (size_t)L.R6 * kHidden * sizeof(bf16), s));
