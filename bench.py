@@ -155,9 +155,11 @@ def run_reference_arm(args):
                    f"({tot_audio / K:.0f} audio-s per step), HF SpeechT5 module fp32, batch_size=2 padding=longest loop, warm shapes")
     print(json.dumps({
         "impl": "reference", "metric": "audio_seconds_per_second", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
-        "steps": K, "warmup": W, "ms_per_step": 1e3 * tot_t / K, "higher_is_better": True, "scaling": "weak",
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * tot_t / K, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(n=args.utts), "device": "cpu", "batch_size": 2, "padding": "longest"},
+        # the workload of the loco arm, named the same way; how the reference runs it (CPU, batch_size=2, padding="longest",
+        # bounded sample) is in cpu_baseline.sample, not in config, so that the two arms' configs compare equal on `workload`
+        "config": {"workload": WORKLOAD.format(n=args.utts)},
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample_desc},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
