@@ -16,6 +16,7 @@ ABI_VERSION = 2
 CSRC = os.path.join(_HERE, "csrc")
 
 LOCO_F32, LOCO_F16, LOCO_BF16, LOCO_F64 = 0, 1, 2, 3
+LOCO_OK, LOCO_ERR_INVALID, LOCO_ERR_CUDA, LOCO_ERR_WEIGHTS, LOCO_ERR_WORKSPACE, LOCO_ERR_STATE = 0, -1, -2, -3, -4, -5   # loco_status
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 EPI_LN_BIAS, EPI_LN_BIAS_GELU, EPI_BIAS_RESIDUAL_STATS, EPI_BIAS_LNRESIDUAL_STATS = 3, 4, 5, 6
 

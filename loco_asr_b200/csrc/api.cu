@@ -631,7 +631,9 @@ int loco_create(const loco_config* cfg, int device, loco_handle** out) {
     h->cfg = *cfg;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
-    if (const char* e = getenv("LOCO_ATTN_P2_MAX_FRAMES")) h->attn_p2_max_frames = atoi(e);     // A/B runs (tools/): 0 = one-item kernel only
+#ifdef LOCO_DEBUG
+    if (const char* e = getenv("LOCO_ATTN_P2_MAX_FRAMES")) h->attn_p2_max_frames = atoi(e);     // A/B runs: 0 = one-item kernel only
+#endif
     int rc = tensormap_init();
     if (!rc) rc = gemm_tc2_init();
     if (!rc) rc = attention_tc_init();
@@ -665,7 +667,9 @@ void loco_destroy(loco_handle* h) {
 
 static int load_tensor_impl(loco_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype);
 int loco_load_tensor(loco_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype) {
-    if (!h || !key || !data || ndim < 0 || ndim > 4) return fail(h, LOCO_ERR_INVALID, "loco_load_tensor: bad argument");
+    if (!h || !key || !data || ndim < 0 || ndim > 4 || (ndim > 0 && !shape)) return fail(h, LOCO_ERR_INVALID, "loco_load_tensor: bad argument");
+    for (int i = 0; i < ndim; ++i)
+        if (shape[i] < 0 || shape[i] > ((int64_t)1 << 31)) return fail(h, LOCO_ERR_INVALID, "loco_load_tensor: bad shape");
     return guarded(h, "loco_load_tensor", [&]() -> int { return load_tensor_impl(h, key, data, shape, ndim, dtype); });
 }
 static int load_tensor_impl(loco_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype) {
@@ -1481,8 +1485,12 @@ int loco_profile_collect(loco_handle* h, int n_cats, double* ms, int64_t* launch
     return LOCO_OK;
 }
 
+static int set_head_impl(loco_handle* h, int method, const float* q_host, const float* w_host, const float* b_host, int n_classes);
 int loco_set_head(loco_handle* h, int method, const float* q_host, const float* w_host, const float* b_host, int n_classes) {
     if (!h) return LOCO_ERR_INVALID;
+    return guarded(h, "loco_set_head", [&]() -> int { return set_head_impl(h, method, q_host, w_host, b_host, n_classes); });
+}
+static int set_head_impl(loco_handle* h, int method, const float* q_host, const float* w_host, const float* b_host, int n_classes) {
     if (method < kPoolAverage || method > kPoolAttention) return fail(h, LOCO_ERR_INVALID, "loco_set_head: method must be 0 (average), 1 (max) or 2 (self_attention)");
     if (method == kPoolAttention && !q_host) return fail(h, LOCO_ERR_INVALID, "loco_set_head: self_attention pooling needs q");
     if ((w_host == nullptr) != (b_host == nullptr) || (w_host && n_classes <= 0) || n_classes < 0)

@@ -409,7 +409,7 @@ def main(argv=None):
                    help="write the pooled [1, 768] vector instead of the reference's [T, 768] (recorded in the file as 'pooling')")
     p.add_argument("--full-sequence", action="store_true", help="(default) write [T, 768] like the reference")
     p.add_argument("--decoders", type=int, default=8, help="waveform decode threads")
-    p.add_argument("--writers", type=int, default=2, help="pickle writer threads (tasks are whole chunks of files)")
+    p.add_argument("--writers", type=int, default=2, help="pickle writer processes (tasks are whole chunks of files)")
     p.add_argument("--report", help="write a JSON throughput report of this run (utterances, audio-s, seconds, files) to this path")
     p.add_argument("--synthetic", type=int, default=0, help="use N synthetic SLURP-shaped utterances and random-init weights")
     p.add_argument("--synthetic-decoder", choices=["synth", "slice"], default="synth",

@@ -34,6 +34,31 @@ def test_library_exports_every_declared_symbol():
         assert s in declared_symbols()
 
 
+def test_status_and_dtype_codes_match_the_header():
+    """The binding's numeric codes are the header's enums (loco_status, loco_dtype, LOCO_POOL_*), and null handles / null
+    arguments come back as LOCO_ERR_INVALID without a device (no compute is called here)."""
+    text = open(os.path.join(ROOT, "include", "loco_asr.h")).read()
+    enums = dict(re.findall(r"\b(LOCO_(?:OK|ERR_\w+|F32|F16|BF16|F64))\s*=\s*(-?\d+)", text))
+    for name, val in enums.items():
+        assert getattr(_lib, name) == int(val), name
+    assert len(enums) == 10
+    assert int(re.search(r"#define LOCO_ABI_VERSION (\d+)", text).group(1)) == _lib.ABI_VERSION
+    lib = _lib.load()
+    ws = C.c_size_t()
+    assert lib.loco_finalize_weights(None) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_plan(None, None, 0, None, None, None, C.byref(ws)) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_encode(None, None, None, 0, None, None, None, 0, None) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_encode_text(None, None, None, 0, None, None, None, 0, None) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_encode_host(None, None, None, 0, None, None, None, 0, None) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_plan_info(None, None, None, None, None) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_set_head(None, 0, None, None, None, 0) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_sync_check(None, None) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_launch_count(None) == 0
+    lib.loco_destroy(None)
+    lib.loco_plan_destroy(None, None)
+    assert lib.loco_create(None, 0, None) == _lib.LOCO_ERR_INVALID and b"null" in lib.loco_last_error(None)
+
+
 def test_product_library_ships_only_product_kernels():
     """The cross-check kernels (SIMT GEMM, single-CTA tcgen05 GEMM, mma.sync positional conv and attention) live only in the
     LOCO_DEBUG twin; the product library's device code does not contain them, and its attention path has no mma.sync."""

@@ -181,6 +181,46 @@ def test_too_short_and_empty_inputs(encoder):
     assert out.shape == (0, 768)
 
 
+def test_c_abi_rejects_bad_arguments_with_a_code_and_a_message(weights):
+    """include/loco_asr.h: 'every function returns 0 or a negative loco_status ... nothing throws, nothing calls exit()'.
+    Null pointers, negative shapes and out-of-range counts come back as LOCO_ERR_INVALID with text in loco_last_error."""
+    import ctypes as C
+    from loco_asr_b200 import _lib
+    from loco_asr_b200.encoder import LocoSpeechT5Encoder
+    enc = LocoSpeechT5Encoder(device="cuda:0")
+    lib, h = enc._lib, enc._h
+    data = (C.c_float * 8)()
+    shape = (C.c_int64 * 1)(8)
+    key = b"wrapped_encoder.layer_norm.weight"
+    assert lib.loco_load_tensor(h, key, C.c_void_p(C.addressof(data)), None, 1, _lib.LOCO_F32) == _lib.LOCO_ERR_INVALID
+    bad = (C.c_int64 * 1)(-8)
+    assert lib.loco_load_tensor(h, key, C.c_void_p(C.addressof(data)), bad, 1, _lib.LOCO_F32) == _lib.LOCO_ERR_INVALID
+    assert b"bad shape" in lib.loco_last_error(h)
+    assert lib.loco_load_tensor(h, key, C.c_void_p(C.addressof(data)), shape, 1, 99) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_load_tensor(h, None, C.c_void_p(C.addressof(data)), shape, 1, _lib.LOCO_F32) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_load_tensor(h, b"decoder.x", C.c_void_p(C.addressof(data)), shape, 1, _lib.LOCO_F32) == _lib.LOCO_ERR_WEIGHTS
+    ws = C.c_size_t()
+    ns = (C.c_int32 * 1)(16000)
+    assert lib.loco_plan(h, ns, -1, None, None, None, C.byref(ws)) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_plan(h, ns, 70000, None, None, None, C.byref(ws)) == _lib.LOCO_ERR_INVALID       # > 65535 utterances per call
+    assert lib.loco_plan(h, None, 1, None, None, None, C.byref(ws)) == _lib.LOCO_ERR_INVALID
+    # encode before finalize: a state error, not a crash
+    assert lib.loco_encode(h, None, ns, 1, None, None, None, 0, None) == _lib.LOCO_ERR_STATE
+    enc.load_state_dict(weights)
+    enc.finalize()
+    assert lib.loco_load_tensor(h, key, C.c_void_p(C.addressof(data)), shape, 1, _lib.LOCO_F32) == _lib.LOCO_ERR_STATE
+    assert lib.loco_encode(h, None, ns, 1, None, None, None, 0, None) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_set_head(h, 7, None, None, None, 0) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_set_head(h, 2, None, None, None, 0) == _lib.LOCO_ERR_INVALID                       # self_attention needs q
+    assert lib.loco_set_head(h, 0, None, C.c_void_p(C.addressof(data)), None, 1) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_encode_planned(h, None, None, None, None, None, 0, None) == _lib.LOCO_ERR_INVALID
+    assert lib.loco_sync_check(h, None) == 0
+    # the handle still works after all of that
+    w = synth_wave(16000, 3, 0)
+    out = enc.encode_packed(torch.from_numpy(w).cuda(), [16000])
+    assert torch.isfinite(out).all()
+
+
 def test_batch_composition_does_not_change_an_utterance(encoder):
     """Size-independent property: an utterance's result is bit-identical alone, in a small batch, at another
     position, and inside a large (~20k-frame) batch -- no padding or neighbour leaks anywhere in the path."""
