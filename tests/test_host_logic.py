@@ -222,3 +222,59 @@ def test_conv0_split_gemm_algebra():
     # one bf16 pass alone is two orders worse: the split is what buys fp32-like accuracy
     one = x_hi.astype(np.float64) @ w_hi.T.astype(np.float64) + shift[None, :]
     assert np.abs(one - ref).max() > 30 * np.abs(got - ref).max()
+
+
+def test_deferred_layernorm_fold_algebra():
+    """api.cu finalize_impl `fold` + the EPI_LN_BIAS epilogue restated in numpy: with W' = bf16(gamma (.) W), c1[n] = sum_k W'[n, k]
+    (of the ROUNDED W') and c2 = W beta + b, `rstd_r (u W'^T - mean_r c1) + c2` is LayerNorm(u) W^T + b up to the bf16 rounding of W'
+    alone -- the mean term cancels exactly because c1 sums what the MMA multiplies.  Also the residual form the following GEMM
+    reads: (R - mean) rstd gamma with beta folded into its bias."""
+    def bf16(a):
+        return torch.from_numpy(np.asarray(a, dtype=np.float32)).bfloat16().float().numpy().astype(np.float64)
+    rng = np.random.default_rng(11)
+    M, K, N = 64, 768, 96
+    u = bf16(rng.standard_normal((M, K)) * 1.7 + 40.0)               # un-normalised residual sums as the GEMM reads them (bf16), large common offset
+    W = rng.standard_normal((N, K)) * 0.05
+    b = rng.standard_normal(N)
+    gamma = 0.5 + rng.random(K) * 2
+    beta = rng.standard_normal(K)
+    mean = u.mean(1, keepdims=True)
+    rstd = 1.0 / np.sqrt(u.var(1, keepdims=True) + 1e-5)
+    Wf = bf16(W * gamma[None, :])
+    c1 = Wf.sum(1)
+    c2 = W @ beta + b
+    got = rstd * (u @ Wf.T - mean * c1[None, :]) + c2[None, :]
+    ln = (u - mean) * rstd
+    assert np.abs(got - (ln @ Wf.T + c2[None, :])).max() < 1e-9       # exact identity (fp64): the 40.0 offset cancels
+    ref = (ln * gamma + beta) @ W.T + b                              # LayerNorm then Linear, as HF computes it
+    bound = 2.0 ** -8 * (np.abs(ln) @ np.abs(W * gamma[None, :]).T) + 1e-9
+    assert np.all(np.abs(got - ref) <= bound)                        # what is left is the rounding of W' to bf16
+    # c1 from the UNROUNDED product would leave mean * (sum W' - sum gamma W) * rstd behind: visible with the 40.0 offset
+    c1_bad = (W * gamma[None, :]).sum(1)
+    bad = rstd * (u @ Wf.T - mean * c1_bad[None, :]) + c2[None, :]
+    assert np.abs(bad - ref).max() > 5 * np.abs(got - ref).max()
+    # residual read of the next GEMM (EPI_BIAS_LNRESIDUAL_STATS): out = acc + bias' + (R - mean) rstd gamma, bias' = bias + beta
+    acc = rng.standard_normal((M, K))
+    bias = rng.standard_normal(K)
+    out = acc + (bias + beta)[None, :] + (u - mean) * rstd * gamma[None, :]
+    assert np.abs(out - (acc + bias[None, :] + (ln * gamma + beta))).max() < 1e-9
+
+
+def test_sliced_row_statistics_merge_to_the_row_statistics():
+    """The producers write (mean, M2) per 128-column slice of a 768-wide row ([R6, 6, 2] fp32, no atomics); readers merge the six
+    with Chan's formula.  The merge equals the two-pass mean / variance of the whole row, also with a large common offset."""
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((50, 768)) * 3.0 + 1000.0
+    sl = x.reshape(50, 6, 128)
+    m_s = sl.mean(2)
+    M2_s = ((sl - m_s[..., None]) ** 2).sum(2)
+    n, mean, M2 = 0.0, np.zeros(50), np.zeros(50)
+    for s in range(6):
+        nb = 128.0
+        d = m_s[:, s] - mean
+        tot = n + nb
+        mean = mean + d * nb / tot
+        M2 = M2 + M2_s[:, s] + d * d * n * nb / tot
+        n = tot
+    assert np.abs(mean - x.mean(1)).max() < 1e-9
+    assert np.abs(M2 / 768.0 - x.var(1)).max() < 1e-8
