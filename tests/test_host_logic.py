@@ -278,3 +278,54 @@ def test_sliced_row_statistics_merge_to_the_row_statistics():
         n = tot
     assert np.abs(mean - x.mean(1)).max() < 1e-9
     assert np.abs(M2 / 768.0 - x.var(1)).max() < 1e-8
+
+
+def test_lazy_rescale_online_softmax_algebra():
+    """The attention kernels' softmax restated in numpy (attention_p2.cu / attention_tc.cu): scores in log2 units, 64-key blocks,
+    the running maximum moves only when a block's maximum exceeds it by more than 8 (LOCO_LAZY_RESCALE; P may reach 2^8), P is
+    rounded to bf16 BEFORE it is both multiplied into O and summed into l (l = P . 1 on the tensor core), out = O / l.  Whatever
+    the rescale schedule -- every new maximum, the lazy rule, or the lazy rule voted per 32-row warp -- the result is the exact
+    softmax(S) V up to the bf16 rounding of P, and the weights that were applied sum to exactly one."""
+    def bf16(a):
+        return torch.from_numpy(np.asarray(a, dtype=np.float32)).bfloat16().float().numpy().astype(np.float64)
+    rng = np.random.default_rng(21)
+    R, T, D, FK = 64, 333, 64, 64
+    S = rng.standard_normal((R, T)) * 6.0 + np.linspace(0, 30, T)[None, :]     # maxima keep growing along the keys: many rescales
+    V = bf16(rng.standard_normal((T, D)))
+    ref = np.exp2(S - S.max(1, keepdims=True))
+    ref = (ref / ref.sum(1, keepdims=True)) @ V
+
+    def run(threshold, warp_vote):
+        m = np.full(R, -np.inf)
+        O = np.zeros((R, D))
+        l = np.zeros(R)
+        n_rescales = 0
+        for j in range(0, T, FK):
+            s = S[:, j:j + FK]
+            bm = s.max(1)
+            trig = bm > m + threshold
+            if warp_vote:                                   # __any_sync: one row's trigger moves every row of its 32-row warp
+                trig = np.repeat(trig.reshape(-1, 32).any(1), 32)
+            mx = np.where(trig, np.maximum(m, bm), m)
+            with np.errstate(invalid="ignore"):
+                corr = np.where(trig, np.exp2(m - mx), 1.0)
+            corr = np.where(np.isnan(corr), 0.0, corr)      # first block: exp2(-inf - x) = 0
+            n_rescales += int(trig.sum())
+            O *= corr[:, None]
+            l *= corr
+            m = mx
+            P = bf16(np.exp2(s - m[:, None]))
+            assert P.max() <= 2.0 ** threshold * 1.01 + 1.0
+            O += P @ V[j:j + FK]
+            l += P.sum(1)
+        return O / l[:, None], n_rescales
+
+    eager, n_eager = run(0.0, False)
+    lazy, n_lazy = run(8.0, False)
+    voted, n_voted = run(8.0, True)
+    assert n_lazy < n_eager and n_lazy <= n_voted
+    scale = np.abs(ref).max()
+    for out in (eager, lazy, voted):
+        assert np.abs(out - ref).max() <= 2.0 ** -8 * scale * 2
+    # the three schedules differ only by roundings of P (2^-9 relative each), never by the schedule itself
+    assert np.abs(lazy - eager).max() <= 2.0 ** -8 * scale * 2
