@@ -329,3 +329,35 @@ def test_lazy_rescale_online_softmax_algebra():
         assert np.abs(out - ref).max() <= 2.0 ** -8 * scale * 2
     # the three schedules differ only by roundings of P (2^-9 relative each), never by the schedule itself
     assert np.abs(lazy - eager).max() <= 2.0 ** -8 * scale * 2
+
+
+def test_groupnorm_statistics_from_waveform_moments():
+    """frontend.cu: conv0 is linear with 10 taps and stride 5, so GroupNorm's per-channel mean / biased variance over the T0 output
+    frames (HF modeling_speecht5.py:277-281) follow from 10 first and 55 second moments of the WAVEFORM -- no pass over the
+    512 x T0 conv output.  Restated in numpy (fp64 reduction, as the kernel's) against torch's conv1d + GroupNorm statistics."""
+    rng = np.random.default_rng(5)
+    n = 16000 + 7                                                     # ragged tail: samples past the last frame's taps are unused
+    x = (rng.standard_normal(n) * 0.1 + 0.03).astype(np.float32)     # a DC offset makes the mean term matter
+    w = (rng.standard_normal((512, 10)) * 0.3).astype(np.float32)
+    t0 = (n - 10) // 5 + 1
+    taps = np.stack([x[k: k + 5 * (t0 - 1) + 1: 5] for k in range(10)]).astype(np.float64)     # [10, T0]: x[5 t + k]
+    m1 = taps.mean(1)                                                 # 10 first moments
+    iu = np.triu_indices(10)
+    m2 = (taps[iu[0]] * taps[iu[1]]).mean(1)                          # 55 second moments R_kk', k <= k'
+    assert m2.shape == (55,)
+    R = np.zeros((10, 10))
+    R[iu] = m2
+    R = R + R.T - np.diag(np.diag(R))
+    wd = w.astype(np.float64)
+    mean = wd @ m1
+    var = np.einsum("ck,kl,cl->c", wd, R, wd) - mean ** 2
+    y = torch.nn.functional.conv1d(torch.from_numpy(x).double()[None, None], torch.from_numpy(w).double()[:, None, :], stride=5)[0]
+    assert y.shape == (512, t0)
+    assert np.abs(mean - y.mean(1).numpy()).max() < 1e-12
+    assert np.abs(var - y.var(1, unbiased=False).numpy()).max() < 1e-12
+    # the folded form conv0_tc.cu consumes: y_norm = scale_c * conv(x, w_c) + shift_c
+    gamma, beta = rng.standard_normal(512), rng.standard_normal(512)
+    scale = gamma / np.sqrt(var + 1e-5)
+    shift = beta - mean * scale
+    gn = torch.nn.functional.group_norm(y[None], 512, torch.from_numpy(gamma), torch.from_numpy(beta), eps=1e-5)[0].numpy()
+    assert np.abs(scale[:, None] * y.numpy() + shift[:, None] - gn).max() < 1e-9
