@@ -361,3 +361,27 @@ def test_groupnorm_statistics_from_waveform_moments():
     shift = beta - mean * scale
     gn = torch.nn.functional.group_norm(y[None], 512, torch.from_numpy(gamma), torch.from_numpy(beta), eps=1e-5)[0].numpy()
     assert np.abs(scale[:, None] * y.numpy() + shift[:, None] - gn).max() < 1e-9
+
+
+def test_strided_conv_as_overlapping_row_gemm():
+    """conv1-6 (HF modeling_speecht5.py:210-228: Conv1d(512, 512, k, stride 2, no bias) on a channel-major tensor) as the GEMM
+    api.cu launches on the TIME-MAJOR activation [T_in, 512]: row t of the A operand is the contiguous strip of k input frames
+    starting at frame 2t (row stride lda = 2 * 512, K = k * 512 -- consecutive rows overlap), and the weight is re-laid
+    [out][tap * 512 + in] (api.cu finalize_impl).  Same numbers as torch's conv1d for k = 3 and k = 2."""
+    rng = np.random.default_rng(9)
+    C = 512
+    for k, t_in in ((3, 41), (2, 30), (3, 40)):
+        x = rng.standard_normal((t_in, C))                                  # time-major, as the kernels store it
+        w = rng.standard_normal((C, C, k)) * 0.05                           # HF layout [out][in][tap]
+        t_out = (t_in - k) // 2 + 1
+        flat = x.reshape(-1)
+        lda = 2 * C
+        A = np.lib.stride_tricks.as_strided(flat, shape=(t_out, k * C), strides=(lda * flat.itemsize, flat.itemsize))
+        Wg = w.transpose(0, 2, 1).reshape(C, k * C)                          # [out][tap * 512 + in]
+        got = A @ Wg.T
+        ref = torch.nn.functional.conv1d(torch.from_numpy(x.T.copy())[None], torch.from_numpy(w), stride=2)[0].numpy().T
+        assert ref.shape == (t_out, C)
+        assert np.abs(got - ref).max() < 1e-9
+        # rows the GEMM may touch past the last frame: (t_out - 1) * lda + k * C <= t_in * C, so the 8 zeroed pad frames api.cu
+        # appends to every conv buffer are only ever read by the slot-padding rows, never by a valid output frame
+        assert (t_out - 1) * lda + k * C <= t_in * C
